@@ -1,0 +1,161 @@
+"""ctypes front-end of oracle/liblbm_oracle.so (TEST INFRASTRUCTURE ONLY — see lbm_oracle.c).
+
+`Oracle` mirrors the method names of the reference's `pub struct LBM` (lbm-wgpu/src/lbm.rs:32-98,
+methods :726, :1065, :1076, :1090, :1118, :1127, :1337-1365, :1502) so parity tests read like the
+product's API.  PARITY UNPINNED: the reference has no golden vectors and cannot be run here.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblbm_oracle.so")
+
+POP_NAMES = ("nw", "n", "ne", "w", "rest", "e", "sw", "s", "se")  # lbm.rs:632-640
+CURL, UX, UY, RHO, SPEED = range(5)  # lbm.rs:10-16
+
+
+def build(force=False):
+    """Compile the C oracle in place (gcc, a second or two)."""
+    src = os.path.join(_HERE, "lbm_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        P = C.c_void_p
+        L.lbm_oracle_create.restype = P
+        L.lbm_oracle_create.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float]
+        L.lbm_oracle_destroy.argtypes = [P]
+        for name in ("collide", "stream", "step", "reset_barrier", "reset_to_equilibrium"):
+            getattr(L, "lbm_oracle_" + name).argtypes = [P]
+            getattr(L, "lbm_oracle_" + name).restype = None
+        L.lbm_oracle_iterate.argtypes = [P, C.c_uint32]
+        L.lbm_oracle_summary.argtypes = [P, C.c_int]
+        L.lbm_oracle_set_summary.argtypes = [P, C.c_int]
+        L.lbm_oracle_draw_points.argtypes = [P, P, C.c_size_t]
+        L.lbm_oracle_set_omega.argtypes = [P, C.c_float]
+        L.lbm_oracle_custom_speed.argtypes = [P, C.c_float]
+        L.lbm_oracle_single_cell.argtypes = [P, C.c_uint32]
+        L.lbm_oracle_cell_class.argtypes = [P, P]
+        L.lbm_oracle_set_equil.argtypes = [C.c_float, C.c_float, C.c_float, P]
+        L.lbm_oracle_population.restype = P
+        L.lbm_oracle_population.argtypes = [P, C.c_int, C.c_int]
+        for name in ("barrier", "mx", "my", "rho", "output"):
+            getattr(L, "lbm_oracle_" + name).restype = P
+            getattr(L, "lbm_oracle_" + name).argtypes = [P]
+        L.lbm_oracle_compute_num.restype = C.c_uint64
+        L.lbm_oracle_compute_num.argtypes = [P]
+        L.lbm_oracle_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def set_equil(ux, uy, rho):
+    out = np.zeros(9, np.float32)
+    lib().lbm_oracle_set_equil(ux, uy, rho, out.ctypes.data)
+    return out
+
+
+def threads():
+    return lib().lbm_oracle_threads()
+
+
+class Oracle:
+    def __init__(self, omega, x, y, inflow_ux=0.1):
+        self.w, self.h = int(x), int(y)
+        self._L = lib()
+        self._h = self._L.lbm_oracle_create(self.w, self.h, float(omega), float(inflow_ux))
+        if not self._h:
+            raise MemoryError("lbm_oracle_create failed")
+
+    def close(self):
+        if self._h:
+            self._L.lbm_oracle_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _view(self, ptr, dtype):
+        n = self.w * self.h
+        buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(self.h, self.w)
+
+    # --- the reference's API surface ---
+    def iterate(self, n):
+        self._L.lbm_oracle_iterate(self._h, int(n))
+
+    def collide(self):
+        self._L.lbm_oracle_collide(self._h)
+
+    def stream(self):
+        self._L.lbm_oracle_stream(self._h)
+
+    def step(self):
+        self._L.lbm_oracle_step(self._h)
+
+    def set_summary(self, stat):
+        self._L.lbm_oracle_set_summary(self._h, int(stat))
+
+    def compute_summary(self, stat):
+        self._L.lbm_oracle_summary(self._h, int(stat))
+
+    def draw_points(self, pairs):
+        a = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1)
+        assert a.size % 2 == 0
+        self._L.lbm_oracle_draw_points(self._h, a.ctypes.data, a.size // 2)
+
+    def reset_barrier(self):
+        self._L.lbm_oracle_reset_barrier(self._h)
+
+    def update_omega_buffer(self, omega):
+        self._L.lbm_oracle_set_omega(self._h, float(omega))
+
+    def reset_to_equilibrium(self):
+        self._L.lbm_oracle_reset_to_equilibrium(self._h)
+
+    def custom_speed(self, ux):
+        self._L.lbm_oracle_custom_speed(self._h, float(ux))
+
+    def single_cell(self, index):
+        self._L.lbm_oracle_single_cell(self._h, int(index))
+
+    def get_compute_num(self):
+        return int(self._L.lbm_oracle_compute_num(self._h))
+
+    # --- read-back (views into the oracle's memory; copy if you need to keep them) ---
+    def population(self, buffer, k):
+        """data_buffers[buffer][k]; buffer -1 = the live one (compute_step % 2).  k=4 (rest) always
+        reads buffer 0, the only rest array the reference binds (lbm.rs:775-778)."""
+        if buffer < 0:
+            buffer = self.get_compute_num() % 2
+        if k == 4:
+            buffer = 0
+        return self._view(self._L.lbm_oracle_population(self._h, buffer, k), np.float32)
+
+    def barrier(self):
+        return self._view(self._L.lbm_oracle_barrier(self._h), np.uint32)
+
+    def moments(self):
+        return (self._view(self._L.lbm_oracle_mx(self._h), np.float32),
+                self._view(self._L.lbm_oracle_my(self._h), np.float32),
+                self._view(self._L.lbm_oracle_rho(self._h), np.float32))
+
+    def output(self):
+        return self._view(self._L.lbm_oracle_output(self._h), np.float32)
+
+    def cell_class(self):
+        out = np.zeros((self.h, self.w), np.uint16)
+        self._L.lbm_oracle_cell_class(self._h, out.ctypes.data)
+        return out
