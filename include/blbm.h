@@ -1,0 +1,199 @@
+/*
+ * blbm.h — C ABI of the B200-native lattice update that replaces lbm-wgpu's WGSL pipeline.
+ *
+ * The drop-in boundary is the reference's `pub struct LBM` (lbm-wgpu/src/lbm.rs:32-98).  Every entry
+ * point below names the reference method or pass it replaces; `&Driver` (lbm-wgpu/src/driver.rs:1-7,
+ * wgpu device + queue + surface) has no counterpart — the handle owns a CUDA device, one stream and
+ * all device buffers.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - Every call returns BLBM_OK (0) or a negative blbm_status; blbm_last_error() gives the text of
+ *     the last failure on the calling thread.  The reference panics instead (expect/unwrap).
+ *   - A handle is not thread-safe (the reference's mutators take &mut self, single-threaded wasm).
+ *   - Mutators enqueue on the handle's stream and return; blbm_read_* and blbm_synchronize wait.
+ *   - Host buffers passed in are copied before the call returns (like queue.write_buffer,
+ *     lbm.rs:1342-1343); the caller keeps ownership.
+ *   - Cell index i = x + y*W, y = 0 is the top row, north = -W, east = +1 (lbm.rs:607-609).
+ *   - Population order (lbm.rs:632-640): 0 nw, 1 n, 2 ne, 3 w, 4 rest, 5 e, 6 sw, 7 s, 8 se.
+ *   - There is no CPU fallback: without a CUDA device every call fails with BLBM_ENOGPU.
+ *
+ * A handle simulates a *slab*: rows [row_begin, row_end) of a W x H_global lattice on one GPU.
+ * blbm_create() makes the whole-lattice slab.  Slabs of one lattice are linked to their neighbours
+ * (same process: blbm_link_local; other process: blbm_export_peer / blbm_link_peer) and then exchange
+ * the one-row halos of the three crossing populations per face by direct NVLink stores issued from
+ * the step kernel itself.  Read-backs and writes address the slab's own rows only.
+ */
+#ifndef BLBM_H
+#define BLBM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct blbm blbm_t;
+
+typedef enum blbm_status {
+    BLBM_OK = 0,
+    BLBM_EINVAL = -1, /* bad argument */
+    BLBM_ENOMEM = -2, /* host or device allocation failed */
+    BLBM_ECUDA = -3,  /* a CUDA call failed; see blbm_last_error() */
+    BLBM_ENOGPU = -4, /* no usable CUDA device */
+    BLBM_ESTATE = -5, /* call not valid in the handle's current state */
+    BLBM_EPEER = -6   /* halo peer missing / timed out */
+} blbm_status;
+
+/* SummaryStat, lbm.rs:10-16 (same order) */
+typedef enum blbm_stat { BLBM_CURL = 0, BLBM_UX = 1, BLBM_UY = 2, BLBM_RHO = 3, BLBM_SPEED = 4 } blbm_stat;
+
+/* index into data_buffers[b][k], lbm.rs:632-640 */
+typedef enum blbm_pop {
+    BLBM_NW = 0, BLBM_N = 1, BLBM_NE = 2, BLBM_W = 3, BLBM_REST = 4,
+    BLBM_E = 5, BLBM_SW = 6, BLBM_S = 7, BLBM_SE = 8
+} blbm_pop;
+
+/* step-kernel implementations (all bit-identical; selectable for A/B measurement) */
+typedef enum blbm_kernel {
+    BLBM_KERNEL_AUTO = 0,
+    BLBM_KERNEL_SCALAR = 1, /* one cell per thread, 32-bit accesses */
+    BLBM_KERNEL_VEC4 = 2,   /* four cells per thread, 128-bit accesses, shuffle-realigned x+-1 gathers */
+    BLBM_KERNEL_TMA = 3     /* TMA (cp.async.bulk.tensor) staged tiles, mbarrier pipeline */
+} blbm_kernel;
+
+#define BLBM_PEER_HANDLE_BYTES 512
+
+const char *blbm_last_error(void);
+int blbm_abi_version(void);
+/* number of CUDA devices visible, or a negative blbm_status */
+int blbm_device_count(void);
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+
+/* LBM::new(&driver, omega, x, y), lbm.rs:726 — populations = set_equil(inflow_ux, 0, 1) (lbm.rs:611-643;
+ * the reference hard-codes inflow_ux = 0.1, lbm.rs:740), barrier = init_barrier (rows 0 and H-1,
+ * lbm.rs:595-605), moments/output zero, compute_step = 0, summary = Curl. */
+int blbm_create(uint32_t w, uint32_t h, float omega, float inflow_ux, int device, blbm_t **out);
+
+/* Same, for rows [row_begin, row_end) of a w x h_global lattice (y-slab decomposition; new — the
+ * reference is single-device).  h_global may exceed 2^32 / w cells in total. */
+int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t row_end, float omega,
+                     float inflow_ux, int device, blbm_t **out);
+
+int blbm_destroy(blbm_t *h);
+
+/* ---- the per-timestep update ----------------------------------------------------------------- */
+
+/* LBM::iterate(&driver, n) minus colour map and render, lbm.rs:1065-1074: n x (collide; stream;
+ * compute_step += 1), then calculate_summary with the current stat; frame_number += 1. */
+int blbm_iterate(blbm_t *h, uint32_t n);
+
+/* n x compute_step() (lbm.rs:1112-1116) and nothing else: no summary, frame_number unchanged.  The
+ * moments of the last step are stored, as after iterate. */
+int blbm_advance(blbm_t *h, uint32_t n);
+
+/* Same work as blbm_iterate, bracketed by CUDA events on the handle's stream; waits for completion and
+ * returns the device time in milliseconds.  (Measurement hook; not in the reference.) */
+int blbm_iterate_timed(blbm_t *h, uint32_t n, float *elapsed_ms);
+
+/* pub fn collide / pub fn stream, lbm.rs:1118-1134: one half-step on the live buffer pair; neither
+ * touches compute_step (only compute_step() does, lbm.rs:1112-1116). */
+int blbm_collide(blbm_t *h);
+int blbm_stream(blbm_t *h);
+
+/* LBM::set_summary, lbm.rs:1061 */
+int blbm_set_summary(blbm_t *h, int stat);
+/* LBM::rerender minus colour map / render, lbm.rs:1104-1110: calculate_summary only; frame_number += 1 */
+int blbm_rerender(blbm_t *h);
+/* set_summary + calculate_summary without touching frame_number (convenience) */
+int blbm_compute_summary(blbm_t *h, int stat);
+
+/* LBM::update_omega_buffer, lbm.rs:1358 — takes effect at the next collide */
+int blbm_set_omega(blbm_t *h, float omega);
+
+/* LBM::reset_to_equilibrium (lbm.rs:1076) and LBM::custom_speed (lbm.rs:1090): both population buffers
+ * <- set_equil(0.1 | ux, 0, 1), compute_step = frame_number = 0, then the two pre-collision passes only
+ * (moments WITHOUT the rest population). */
+int blbm_reset_to_equilibrium(blbm_t *h);
+int blbm_custom_speed(blbm_t *h, float ux);
+
+/* LBM::single_cell(index), lbm.rs:1482-1515: set_equil(0,0,1) and population `index` = 4.0 at a fixed
+ * cell; counters reset; moments untouched.  index > 8 only resets. */
+int blbm_single_cell(blbm_t *h, uint32_t index);
+
+/* ---- barrier mask ---------------------------------------------------------------------------- */
+
+/* LBM::draw_shape -> draw_barrier_updates + barrier_draw.wgsl, lbm.rs:1337-1356: pairs is
+ * [loc0, val0, loc1, val1, ...] as produced by get_points_vector (merge_shapes.rs:12-22); loc is a
+ * GLOBAL cell index, val 1 = barrier, 0 = fluid; out-of-range locations are dropped.  Duplicate
+ * locations: last pair wins (the reference leaves it to the GPU's scatter order; Blob keys are unique).
+ * npairs == 0 is a no-op (the reference underflows, lbm.rs:1343; its callers guard). */
+int blbm_draw_points(blbm_t *h, const uint32_t *loc_val_pairs, size_t npairs);
+/* 64-bit locations for lattices of 2^32 cells and more */
+int blbm_draw_points64(blbm_t *h, const uint64_t *loc_val_pairs, size_t npairs);
+/* LBM::reset_barrier, lbm.rs:1362-1365 */
+int blbm_reset_barrier(blbm_t *h);
+
+/* ---- counters, lbm.rs:1166-1172 ---------------------------------------------------------------- */
+uint64_t blbm_get_compute_num(const blbm_t *h);
+uint64_t blbm_get_frame_num(const blbm_t *h);
+
+/* ---- read-back / restore (absent in the reference, which never reads back; required by "read back
+ *      macroscopic fields" and by the parity tests).  All arrays are rows x W of the slab's own rows,
+ *      densely packed.  dst/src are HOST pointers. ------------------------------------------------ */
+
+/* data_buffers[buffer][k]; buffer 0/1, or -1 = the live one (compute_step % 2).  k = 4 (rest) always
+ * addresses the single rest array (the reference binds data_buffers[0][4] only, lbm.rs:775-778).
+ * Contents are bit-identical to what the reference's buffers hold after the same call sequence,
+ * including the stale values at cells the stream passes skip. */
+int blbm_read_population(blbm_t *h, int buffer, int k, float *dst);
+int blbm_write_population(blbm_t *h, int buffer, int k, const float *src);
+/* density_bg = (momentum x, momentum y, density) of the state before the last collide; any may be NULL */
+int blbm_read_moments(blbm_t *h, float *mx, float *my, float *rho);
+/* output_bg, the array the colour map reads */
+int blbm_read_output(blbm_t *h, float *dst);
+/* barrier_buffer as the reference's u32 0/1 words */
+int blbm_read_barrier(blbm_t *h, uint32_t *dst);
+/* per-cell classification: bit0 barrier, bit1 skipped by stream (barrier | x==0 | y>=H-1), bits 2..9
+ * "upstream neighbour is a barrier" for nw n ne w e sw s se */
+int blbm_read_cell_class(blbm_t *h, uint16_t *dst);
+
+/* Asynchronous variants for frame pipelines: dst must be page-locked (cudaHostAlloc / pinned torch
+ * tensor); the copy is ordered after everything enqueued so far and overlaps later work.  Complete
+ * after blbm_synchronize(). */
+int blbm_read_output_async(blbm_t *h, float *pinned_dst);
+int blbm_synchronize(blbm_t *h);
+
+/* Global reductions over the slab's rows (warp-shuffle + one atomic per block): sum of density, of
+ * both momenta, and max |output|.  sums are double.  (Diagnostics; not in the reference.) */
+int blbm_reduce_moments(blbm_t *h, double *sum_rho, double *sum_mx, double *sum_my, float *max_abs_output);
+
+/* ---- slab geometry and halo peers ------------------------------------------------------------ */
+int blbm_get_geometry(const blbm_t *h, uint32_t *w, uint64_t *h_global, uint64_t *row_begin, uint64_t *row_end,
+                      int *device);
+
+/* Link two slabs living in the SAME process: `upper` owns the rows just above `lower`. */
+int blbm_link_local(blbm_t *upper, blbm_t *lower);
+/* Different processes (one per GPU): export this slab's halo window as an opaque blob
+ * (BLBM_PEER_HANDLE_BYTES bytes, CUDA IPC inside), ship it with any transport, and link the blob of the
+ * slab above (side = 0) or below (side = 1). */
+int blbm_export_peer(blbm_t *h, void *blob);
+int blbm_link_peer(blbm_t *h, int side, const void *blob);
+/* Re-send the boundary rows of both population buffers and of the moments to the linked neighbours
+ * (collective: every slab of the lattice calls it).  Needed only after blbm_write_population; steps,
+ * resets and paints keep halos current by themselves. */
+int blbm_exchange_halos(blbm_t *h);
+
+/* ---- tuning / measurement -------------------------------------------------------------------- */
+int blbm_set_kernel(blbm_t *h, int kernel); /* blbm_kernel */
+int blbm_get_kernel(const blbm_t *h);       /* the resolved implementation (never AUTO) */
+/* kernels launched by this handle since creation (the bench's gpu_launches claim) */
+uint64_t blbm_get_launch_count(const blbm_t *h);
+/* device bytes held by the handle */
+uint64_t blbm_get_device_bytes(const blbm_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLBM_H */

@@ -1,0 +1,1018 @@
+// api.cu — the C ABI of include/blbm.h: handle life cycle, the regime state machine around the fused
+// step kernel, barrier painting, read-back, and the halo peers of y-slab decomposition.
+//
+// State machine.  `step` is the reference's compute_step (lbm.rs:91,1112-1116).
+//   S-regime: both population buffers are bit-identical to the reference's data_buffers.
+//   T-regime: buffer (step-1)%2 holds T_{step-1} (post-collision, every cell); buffer step%2 holds what
+//             the reference's non-live buffer held one step earlier; the stream of step-1 is pending and
+//             is executed by the gather half of the next fused launch (or by materialise()).
+// iterate(n) leaves the handle in the T-regime; anything that must observe or perturb the reference's
+// buffers (read/write population, the public half-steps) materialises first.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <unistd.h>
+#include <vector>
+
+#include "../../include/blbm.h"
+#include "blbm_internal.cuh"
+
+using namespace blbmk;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(BLBM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,    \
+                        __LINE__);                                                                        \
+    } while (0)
+
+#define CKH(h)                                                                  \
+    do {                                                                        \
+        if (!(h)) return fail(BLBM_EINVAL, "null handle");                      \
+        CK(cudaSetDevice((h)->device));                                         \
+    } while (0)
+
+constexpr uint32_t PEER_MAGIC = 0xB1B30001u;
+
+// what a neighbour needs to know to store into our halo rows
+struct PeerBlob {
+    uint32_t magic;
+    uint32_t W, P, rows;
+    uint64_t row0, row1, Hg;
+    uint64_t pool_bytes;
+    uint64_t off_f[2][8];
+    uint64_t off_mx, off_my;
+    uint64_t off_flags;
+    int32_t device;
+    int32_t pid;
+    uint64_t local_ptr;  // pool base in the exporting process (used when pid matches)
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(PeerBlob) <= BLBM_PEER_HANDLE_BYTES, "peer blob too large");
+
+struct Peer {
+    bool linked = false;
+    bool ipc_opened = false;
+    char *base = nullptr;  // neighbour's pool mapped into this process / device
+    PeerBlob info{};
+};
+
+}  // namespace
+
+struct blbm {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t W = 0, P = 0, rows = 0;
+    uint64_t Hg = 0, row0 = 0, row1 = 0;
+    size_t plane = 0;  // elements per population plane, (rows+3)*P
+    char *pool = nullptr;
+    size_t pool_bytes = 0;
+    float *f[2][8] = {};
+    float *R = nullptr, *mx = nullptr, *my = nullptr, *rho = nullptr, *out = nullptr;
+    uint16_t *cls[2] = {};
+    uint8_t *mask = nullptr;
+    unsigned long long *flags = nullptr;  // [0] epoch from the slab above, [16] from below (128 B apart)
+    int *err_flag = nullptr;
+    double *red_sums = nullptr;
+    float *red_max = nullptr;
+    size_t off_f[2][8] = {};
+    size_t off_mx = 0, off_my = 0, off_flags = 0;
+    int cls_cur = 0;
+    bool cls_pending = false;  // the mask changed while a stream was pending: cls[cls_cur^1] is newer
+    bool regimeT = false;
+    bool halo_dirty = false;
+    float omega = 1.0f;
+    int stat = BLBM_CURL;
+    uint64_t step = 0, frame = 0;
+    int kernel = BLBM_KERNEL_VEC4;
+    uint64_t launches = 0;
+    Peer up, dn;
+    unsigned long long epoch = 0, waited = 0;
+    unsigned long long wait_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+    uint64_t *d_pairs = nullptr;
+    size_t d_pairs_cap = 0;
+};
+
+namespace {
+
+SlabGeom geom(const blbm *h)
+{
+    SlabGeom g;
+    g.W = h->W;
+    g.P = h->P;
+    g.rows = h->rows;
+    g.row0 = h->row0;
+    g.Hg = h->Hg;
+    return g;
+}
+
+bool has_up(const blbm *h) { return h->row0 > 0; }
+bool has_dn(const blbm *h) { return h->row1 < h->Hg; }
+
+// remote halo-row pointers for a launch that writes buffer `b`
+PushTargets push_targets(const blbm *h, int b)
+{
+    PushTargets t;
+    memset(&t, 0, sizeof(t));
+    const size_t P = h->P;
+    if (h->up.linked) {
+        const PeerBlob &u = h->up.info;
+        char *base = h->up.base;
+        const size_t halo1 = (size_t)(u.rows + 1) * P, halo2 = (size_t)(u.rows + 2) * P;
+        t.up_n = reinterpret_cast<float *>(base + u.off_f[b][D_N]) + halo1;
+        t.up_ne = reinterpret_cast<float *>(base + u.off_f[b][D_NE]) + halo1;
+        t.up_nw = reinterpret_cast<float *>(base + u.off_f[b][D_NW]) + halo1;
+        t.up_w = reinterpret_cast<float *>(base + u.off_f[b][D_W]) + halo1;
+        t.up_nw2 = reinterpret_cast<float *>(base + u.off_f[b][D_NW]) + halo2;
+        t.up_mx = reinterpret_cast<float *>(base + u.off_mx) + halo1;
+        t.up_my = reinterpret_cast<float *>(base + u.off_my) + halo1;
+    }
+    if (h->dn.linked) {
+        const PeerBlob &d = h->dn.info;
+        char *base = h->dn.base;
+        t.dn_s = reinterpret_cast<float *>(base + d.off_f[b][D_S]);
+        t.dn_se = reinterpret_cast<float *>(base + d.off_f[b][D_SE]);
+        t.dn_sw = reinterpret_cast<float *>(base + d.off_f[b][D_SW]);
+        t.dn_mx = reinterpret_cast<float *>(base + d.off_mx);
+        t.dn_my = reinterpret_cast<float *>(base + d.off_my);
+    }
+    return t;
+}
+
+bool any_peer(const blbm *h) { return h->up.linked || h->dn.linked; }
+
+// Before a kernel that reads halo rows, or stores into a neighbour's: wait until both neighbours have
+// finished the launch that produced the current epoch.
+int sync_peers(blbm *h)
+{
+    if (!any_peer(h) || h->waited >= h->epoch) return BLBM_OK;
+    const unsigned long long *fu = h->up.linked ? h->flags : nullptr;
+    const unsigned long long *fd = h->dn.linked ? h->flags + 16 : nullptr;
+    CK(launch_wait(fu, fd, h->epoch, h->err_flag, h->wait_timeout_ns, h->stream));
+    h->launches++;
+    h->waited = h->epoch;
+    return BLBM_OK;
+}
+
+// After a kernel that stored into neighbours' halo rows: publish a new epoch to them.
+int signal_peers(blbm *h)
+{
+    if (!any_peer(h)) return BLBM_OK;
+    h->epoch++;
+    // our word in the slab above is its "from below" flag, and vice versa
+    unsigned long long *ru =
+        h->up.linked ? reinterpret_cast<unsigned long long *>(h->up.base + h->up.info.off_flags) + 16 : nullptr;
+    unsigned long long *rd =
+        h->dn.linked ? reinterpret_cast<unsigned long long *>(h->dn.base + h->dn.info.off_flags) : nullptr;
+    CK(launch_signal(ru, rd, h->epoch, h->stream));
+    h->launches++;
+    return BLBM_OK;
+}
+
+int push_all_halos(blbm *h);
+
+int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
+{
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    for (int d = 0; d < 8; d++) {
+        p.X[d] = h->f[xbuf][d];
+        p.Y[d] = h->f[ybuf][d];
+    }
+    p.R = h->R;
+    p.cls = h->cls[h->cls_cur];
+    p.mx = h->mx;
+    p.my = h->my;
+    p.rho = h->rho;
+    p.W = h->W;
+    p.P = h->P;
+    p.rows = h->rows;
+    p.row0 = h->row0;
+    p.Hg = h->Hg;
+    p.omega = h->omega;
+    const bool pushes = mode != MODE_STREAM_ONLY;
+    if (pushes) p.push = push_targets(h, ybuf);
+    int rc;
+    if (h->halo_dirty && any_peer(h) && mode != MODE_COLLIDE_ONLY && (rc = push_all_halos(h)) != BLBM_OK) return rc;
+    rc = sync_peers(h);
+    if (rc) return rc;
+    int k = h->kernel;
+    if (mode != MODE_FUSED) k = BLBM_KERNEL_SCALAR;
+    cudaError_t e;
+    switch (k) {
+    case BLBM_KERNEL_SCALAR: e = launch_step_scalar(p, mode, mom, h->stream); break;
+    default: e = launch_step_vec4(p, mode, mom, h->stream); break;
+    }
+    if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches++;
+    if (pushes) return signal_peers(h);
+    return BLBM_OK;
+}
+
+void consume_pending_class(blbm *h)
+{
+    if (h->cls_pending) {
+        h->cls_cur ^= 1;
+        h->cls_pending = false;
+    }
+}
+
+// T-regime -> S-regime: run the pending stream (stream/*.wgsl) so that both buffers equal the reference's
+int materialise(blbm *h)
+{
+    if (!h->regimeT) return BLBM_OK;
+    const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
+    int rc = launch_step(h, MODE_STREAM_ONLY, x, y, false);
+    if (rc) return rc;
+    h->regimeT = false;
+    consume_pending_class(h);
+    return BLBM_OK;
+}
+
+int run_summary(blbm *h)
+{
+    int rc = sync_peers(h);  // curl reads the moment halo rows
+    if (rc) return rc;
+    CK(launch_summary(h->stat, h->mx, h->my, h->rho, h->out, geom(h), h->stream));
+    h->launches++;
+    return BLBM_OK;
+}
+
+int do_steps(blbm *h, uint32_t n)
+{
+    uint32_t left = n;
+    while (left) {
+        const bool mom = left == 1;
+        int rc;
+        if (!h->regimeT) {
+            // collide of step `step`, in place on the live buffer (collision/*.wgsl); its stream stays pending
+            const int y = (int)(h->step % 2);
+            rc = launch_step(h, MODE_COLLIDE_ONLY, y, y, mom);
+            if (rc) return rc;
+            h->regimeT = true;
+        } else {
+            // stream of step-1 fused with collide of step
+            const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
+            rc = launch_step(h, MODE_FUSED, x, y, mom);
+            if (rc) return rc;
+            consume_pending_class(h);
+        }
+        h->step++;
+        left--;
+    }
+    return BLBM_OK;
+}
+
+int rebuild_class(blbm *h)
+{
+    // in the T-regime the pending stream must still see the old classification
+    const int target = h->regimeT ? (h->cls_cur ^ 1) : h->cls_cur;
+    CK(launch_build_class(h->cls[target], h->mask, geom(h), h->stream));
+    h->launches++;
+    if (h->regimeT) h->cls_pending = true;
+    return BLBM_OK;
+}
+
+int fill_equilibrium(blbm *h, float ux, int single_index)
+{
+    // set_equil on the host in fp32 with the reference's op order (lbm.rs:611-643); uy = 0, rho = 1
+    float v9[9];
+    {
+        float uxx = ux, uy = 0.0f, rho = 1.0f;
+        float ux_2 = uxx * uxx, uy_2 = uy * uy;
+        float u_dot = ux_2 + uy_2;
+        float uxuy = uxx * uy;
+        float pos = u_dot + 2.0f * uxuy, neg = u_dot - 2.0f * uxuy;
+        uxx *= 3.0f;
+        uy *= 3.0f;
+        ux_2 *= 4.5f;
+        uy_2 *= 4.5f;
+        u_dot *= 1.5f;
+        neg *= 4.5f;
+        pos *= 4.5f;
+        const float r9 = rho / 9.0f, r36 = rho / 36.0f;
+        v9[BLBM_NW] = r36 * ((((1.0f - uxx) + uy) + neg) - u_dot);
+        v9[BLBM_N] = r9 * (((1.0f + uy) + uy_2) - u_dot);
+        v9[BLBM_NE] = r36 * ((((1.0f + uxx) + uy) + pos) - u_dot);
+        v9[BLBM_W] = r9 * (((1.0f - uxx) + ux_2) - u_dot);
+        v9[BLBM_REST] = (4.0f * r9) * (1.0f - u_dot);
+        v9[BLBM_E] = r9 * (((1.0f + uxx) + ux_2) - u_dot);
+        v9[BLBM_SW] = r36 * ((((1.0f - uxx) - uy) + pos) - u_dot);
+        v9[BLBM_S] = r9 * (((1.0f - uy) - uy_2) - u_dot);
+        v9[BLBM_SE] = r36 * ((((1.0f + uxx) - uy) + neg) - u_dot);
+    }
+    static const int pop_of_dir[8] = {BLBM_NW, BLBM_N, BLBM_NE, BLBM_W, BLBM_E, BLBM_SW, BLBM_S, BLBM_SE};
+    float *planes[17];
+    float vals[17];
+    int n = 0;
+    for (int b = 0; b < 2; b++)
+        for (int d = 0; d < 8; d++) {
+            planes[n] = h->f[b][d];
+            vals[n++] = v9[pop_of_dir[d]];
+        }
+    planes[n] = h->R;
+    vals[n++] = v9[BLBM_REST];
+    // own rows plus the halo rows that belong to a neighbouring slab (rows outside the lattice stay 0)
+    const uint32_t r_begin = has_up(h) ? 0u : 1u;
+    uint32_t r_end = h->rows + 1;
+    if (has_dn(h)) r_end += (uint32_t)std::min<uint64_t>(2, h->Hg - h->row1);
+    CK(launch_fill_rows(planes, vals, n, h->W, h->P, r_begin, r_end, h->stream));
+    h->launches++;
+    if (single_index >= 0 && single_index <= 8) {
+        // set_single_cell, lbm.rs:1482-1500
+        const int64_t x = h->W, y = (int64_t)h->Hg;
+        int64_t cx = 0, cy = 0;
+        switch (single_index) {
+        case 0: cx = x - 2; cy = y - 2; break;
+        case 1: cx = 3 * x / 4; cy = y - 2; break;
+        case 2: cx = x / 3; cy = y - 2; break;
+        case 3: cx = x - 2; cy = y / 2; break;
+        case 4: cx = 3 * x / 4; cy = y / 2; break;
+        case 5: cx = x / 2; cy = y / 2; break;
+        case 6: cx = x - 2; cy = 1; break;
+        case 7: cx = 3 * x / 4; cy = 1; break;
+        default: cx = x / 2; cy = 1; break;
+        }
+        // the reference indexes the flat array with cx + cy*W; negative or past-the-end indices would
+        // panic there, here they are dropped
+        const int64_t flat = cx + cy * x;
+        if (cx >= 0 && cy >= 0 && flat >= 0 && flat < x * y) {
+            const int64_t gy = flat / x, gx = flat % x;
+            const int64_t dr = gy - (int64_t)h->row0 + 1;  // device row
+            if (dr >= (int64_t)r_begin && dr < (int64_t)r_end) {
+                const float four = 4.0f;
+                const size_t off = (size_t)dr * h->P + (size_t)gx;
+                if (single_index == BLBM_REST) {
+                    CK(cudaMemcpyAsync(h->R + off, &four, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+                } else {
+                    int d = 0;
+                    for (int q = 0; q < 8; q++)
+                        if (pop_of_dir[q] == single_index) d = q;
+                    for (int b = 0; b < 2; b++)
+                        CK(cudaMemcpyAsync(h->f[b][d] + off, &four, sizeof(float), cudaMemcpyHostToDevice,
+                                           h->stream));
+                }
+                CK(cudaStreamSynchronize(h->stream));  // `four` lives on this stack frame
+            }
+        }
+    }
+    h->step = 0;
+    h->frame = 0;
+    h->regimeT = false;
+    consume_pending_class(h);
+    h->halo_dirty = false;  // every slab filled its halo rows with the same constants
+    return BLBM_OK;
+}
+
+int moments_without_rest(blbm *h)
+{
+    const uint32_t r_begin = has_up(h) ? 0u : 1u;
+    const uint32_t r_end = h->rows + 1 + (has_dn(h) ? 1u : 0u);
+    const float *f8[8];
+    for (int d = 0; d < 8; d++) f8[d] = h->f[0][d];
+    CK(launch_precollision_moments(f8, h->mx, h->my, h->rho, h->W, h->P, r_begin, r_end, h->stream));
+    h->launches++;
+    return BLBM_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_peer_err(blbm *h)
+{
+    if (!any_peer(h)) return BLBM_OK;
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (e) return fail(BLBM_EPEER, "a neighbouring slab did not reach the expected epoch within the timeout");
+    return BLBM_OK;
+}
+
+int sync_stream(blbm *h)
+{
+    CK(cudaStreamSynchronize(h->stream));
+    return check_peer_err(h);
+}
+
+// push the rows neighbours gather from, for both buffers (used right after linking and after
+// blbm_write_population)
+int push_all_halos(blbm *h)
+{
+    int rc = sync_peers(h);
+    if (rc) return rc;
+    const size_t rowb = (size_t)h->P * sizeof(float);
+    for (int b = 0; b < 2; b++) {
+        PushTargets t = push_targets(h, b);
+        const size_t first = row_off(0, h->P), second = row_off(1, h->P), last = row_off(h->rows - 1, h->P);
+        if (h->up.linked) {
+            CK(cudaMemcpyAsync(t.up_n, h->f[b][D_N] + first, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.up_ne, h->f[b][D_NE] + first, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.up_nw, h->f[b][D_NW] + first, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.up_w, h->f[b][D_W] + first, sizeof(float), cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.up_nw2, h->f[b][D_NW] + second, sizeof(float), cudaMemcpyDefault, h->stream));
+        }
+        if (h->dn.linked) {
+            CK(cudaMemcpyAsync(t.dn_s, h->f[b][D_S] + last, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.dn_se, h->f[b][D_SE] + last, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.dn_sw, h->f[b][D_SW] + last, rowb, cudaMemcpyDefault, h->stream));
+        }
+    }
+    {
+        PushTargets t = push_targets(h, 0);
+        const size_t first = row_off(0, h->P), last = row_off(h->rows - 1, h->P);
+        if (h->up.linked) {
+            CK(cudaMemcpyAsync(t.up_mx, h->mx + first, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.up_my, h->my + first, rowb, cudaMemcpyDefault, h->stream));
+        }
+        if (h->dn.linked) {
+            CK(cudaMemcpyAsync(t.dn_mx, h->mx + last, rowb, cudaMemcpyDefault, h->stream));
+            CK(cudaMemcpyAsync(t.dn_my, h->my + last, rowb, cudaMemcpyDefault, h->stream));
+        }
+    }
+    h->halo_dirty = false;
+    return signal_peers(h);
+}
+
+void fill_blob(const blbm *h, PeerBlob *b)
+{
+    memset(b, 0, sizeof(*b));
+    b->magic = PEER_MAGIC;
+    b->W = h->W;
+    b->P = h->P;
+    b->rows = h->rows;
+    b->row0 = h->row0;
+    b->row1 = h->row1;
+    b->Hg = h->Hg;
+    b->pool_bytes = h->pool_bytes;
+    for (int q = 0; q < 2; q++)
+        for (int d = 0; d < 8; d++) b->off_f[q][d] = h->off_f[q][d];
+    b->off_mx = h->off_mx;
+    b->off_my = h->off_my;
+    b->off_flags = h->off_flags;
+    b->device = h->device;
+    b->pid = (int32_t)getpid();
+    b->local_ptr = (uint64_t)(uintptr_t)h->pool;
+}
+
+int attach_peer(blbm *h, int side, const PeerBlob &b, char *base, bool ipc_opened)
+{
+    Peer &p = side == 0 ? h->up : h->dn;
+    if (p.linked) return fail(BLBM_ESTATE, "side %d already linked", side);
+    if (b.magic != PEER_MAGIC) return fail(BLBM_EINVAL, "bad peer blob");
+    if (b.W != h->W || b.Hg != h->Hg) return fail(BLBM_EINVAL, "peer belongs to a different lattice");
+    if (side == 0 && b.row1 != h->row0) return fail(BLBM_EINVAL, "peer is not the slab directly above");
+    if (side == 1 && b.row0 != h->row1) return fail(BLBM_EINVAL, "peer is not the slab directly below");
+    if (h->rows < 2 || b.rows < 2) return fail(BLBM_EINVAL, "linked slabs need at least 2 rows each");
+    p.linked = true;
+    p.ipc_opened = ipc_opened;
+    p.base = base;
+    p.info = b;
+    return BLBM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *blbm_last_error(void) { return g_err; }
+int blbm_abi_version(void) { return 1; }
+
+int blbm_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(BLBM_ENOGPU, "no CUDA device: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t row_end, float omega,
+                     float inflow_ux, int device, blbm_t **out)
+{
+    if (!out) return fail(BLBM_EINVAL, "out is null");
+    *out = nullptr;
+    if (w == 0 || h_global == 0) return fail(BLBM_EINVAL, "lattice must be at least 1x1");
+    if (row_begin >= row_end || row_end > h_global) return fail(BLBM_EINVAL, "bad row range");
+    if (row_end - row_begin > 0x7ffffff0ull) return fail(BLBM_EINVAL, "slab too tall");
+    if (w > 0x7fffff00u) return fail(BLBM_EINVAL, "rows too long");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(BLBM_ENOGPU, "no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(BLBM_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    CK(cudaSetDevice(device));
+
+    blbm *h = new (std::nothrow) blbm();
+    if (!h) return fail(BLBM_ENOMEM, "out of host memory");
+    h->device = device;
+    h->W = w;
+    h->P = (w + 31u) / 32u * 32u;
+    h->Hg = h_global;
+    h->row0 = row_begin;
+    h->row1 = row_end;
+    h->rows = (uint32_t)(row_end - row_begin);
+    h->plane = (size_t)(h->rows + 3) * h->P;
+    h->omega = omega;
+
+    // one pool, carved into 1 KiB-aligned planes (a single allocation = a single IPC handle)
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 1024);
+        return o;
+    };
+    const size_t pb = h->plane * sizeof(float);
+    for (int b = 0; b < 2; b++)
+        for (int d = 0; d < 8; d++) h->off_f[b][d] = carve(pb);
+    const size_t off_R = carve(pb);
+    h->off_mx = carve(pb);
+    h->off_my = carve(pb);
+    const size_t off_rho = carve(pb), off_out = carve(pb);
+    const size_t off_cls0 = carve(h->plane * sizeof(uint16_t)), off_cls1 = carve(h->plane * sizeof(uint16_t));
+    const size_t off_mask = carve((size_t)(h->rows + 4) * h->P);
+    h->off_flags = carve(256);
+    const size_t off_err = carve(64), off_red = carve(64);
+    h->pool_bytes = off;
+    e = cudaMalloc(&h->pool, h->pool_bytes);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(BLBM_ENOMEM, "cudaMalloc of %zu bytes failed: %s", off, cudaGetErrorString(e));
+    }
+    for (int b = 0; b < 2; b++)
+        for (int d = 0; d < 8; d++) h->f[b][d] = reinterpret_cast<float *>(h->pool + h->off_f[b][d]);
+    h->R = reinterpret_cast<float *>(h->pool + off_R);
+    h->mx = reinterpret_cast<float *>(h->pool + h->off_mx);
+    h->my = reinterpret_cast<float *>(h->pool + h->off_my);
+    h->rho = reinterpret_cast<float *>(h->pool + off_rho);
+    h->out = reinterpret_cast<float *>(h->pool + off_out);
+    h->cls[0] = reinterpret_cast<uint16_t *>(h->pool + off_cls0);
+    h->cls[1] = reinterpret_cast<uint16_t *>(h->pool + off_cls1);
+    h->mask = reinterpret_cast<uint8_t *>(h->pool + off_mask);
+    h->flags = reinterpret_cast<unsigned long long *>(h->pool + h->off_flags);
+    h->err_flag = reinterpret_cast<int *>(h->pool + off_err);
+    h->red_sums = reinterpret_cast<double *>(h->pool + off_red);
+    h->red_max = reinterpret_cast<float *>(h->pool + off_red + 32);
+
+    int rc = BLBM_OK;
+    do {
+        cudaError_t ce;
+        if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+            (ce = cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->stream)) != cudaSuccess) {
+            rc = fail(BLBM_ECUDA, "handle setup failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        if ((rc = fill_equilibrium(h, inflow_ux, -1)) != BLBM_OK) break;
+        if ((ce = launch_mask_init(h->mask, geom(h), h->stream)) != cudaSuccess ||
+            (ce = launch_build_class(h->cls[0], h->mask, geom(h), h->stream)) != cudaSuccess) {
+            rc = fail(BLBM_ECUDA, "mask setup failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        h->launches += 2;
+        if ((ce = cudaStreamSynchronize(h->stream)) != cudaSuccess) {
+            rc = fail(BLBM_ECUDA, "handle setup failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+    } while (0);
+    if (rc != BLBM_OK) {
+        blbm_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return BLBM_OK;
+}
+
+int blbm_create(uint32_t w, uint32_t hgt, float omega, float inflow_ux, int device, blbm_t **out)
+{
+    return blbm_create_slab(w, hgt, 0, hgt, omega, inflow_ux, device, out);
+}
+
+int blbm_destroy(blbm_t *h)
+{
+    if (!h) return BLBM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->up.ipc_opened) cudaIpcCloseMemHandle(h->up.base);
+    if (h->dn.ipc_opened) cudaIpcCloseMemHandle(h->dn.base);
+    if (h->d_pairs) cudaFree(h->d_pairs);
+    if (h->pool) cudaFree(h->pool);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BLBM_OK;
+}
+
+int blbm_iterate(blbm_t *h, uint32_t n)
+{
+    CKH(h);
+    int rc = do_steps(h, n);
+    if (rc) return rc;
+    rc = run_summary(h);
+    if (rc) return rc;
+    h->frame++;
+    return BLBM_OK;
+}
+
+int blbm_advance(blbm_t *h, uint32_t n)
+{
+    CKH(h);
+    return do_steps(h, n);
+}
+
+int blbm_iterate_timed(blbm_t *h, uint32_t n, float *elapsed_ms)
+{
+    CKH(h);
+    if (!elapsed_ms) return fail(BLBM_EINVAL, "elapsed_ms is null");
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int rc = do_steps(h, n);
+    if (rc) return rc;
+    rc = run_summary(h);
+    if (rc) return rc;
+    h->frame++;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    return check_peer_err(h);
+}
+
+int blbm_collide(blbm_t *h)
+{
+    CKH(h);
+    int rc = materialise(h);
+    if (rc) return rc;
+    const int y = (int)(h->step % 2);
+    return launch_step(h, MODE_COLLIDE_ONLY, y, y, true);
+}
+
+int blbm_stream(blbm_t *h)
+{
+    CKH(h);
+    int rc = materialise(h);
+    if (rc) return rc;
+    const int x = (int)(h->step % 2), y = (int)((h->step + 1) % 2);
+    return launch_step(h, MODE_STREAM_ONLY, x, y, false);
+}
+
+int blbm_set_summary(blbm_t *h, int stat)
+{
+    if (!h) return fail(BLBM_EINVAL, "null handle");
+    if (stat < 0 || stat > 4) return fail(BLBM_EINVAL, "stat %d out of range", stat);
+    h->stat = stat;
+    return BLBM_OK;
+}
+
+int blbm_rerender(blbm_t *h)
+{
+    CKH(h);
+    int rc = run_summary(h);
+    if (rc) return rc;
+    h->frame++;
+    return BLBM_OK;
+}
+
+int blbm_compute_summary(blbm_t *h, int stat)
+{
+    CKH(h);
+    int rc = blbm_set_summary(h, stat);
+    if (rc) return rc;
+    return run_summary(h);
+}
+
+int blbm_set_omega(blbm_t *h, float omega)
+{
+    if (!h) return fail(BLBM_EINVAL, "null handle");
+    h->omega = omega;
+    return BLBM_OK;
+}
+
+int blbm_custom_speed(blbm_t *h, float ux)
+{
+    CKH(h);
+    int rc = sync_peers(h);
+    if (rc) return rc;
+    rc = fill_equilibrium(h, ux, -1);
+    if (rc) return rc;
+    return moments_without_rest(h);
+}
+
+int blbm_reset_to_equilibrium(blbm_t *h) { return blbm_custom_speed(h, 0.1f); }
+
+int blbm_single_cell(blbm_t *h, uint32_t index)
+{
+    CKH(h);
+    int rc = sync_peers(h);
+    if (rc) return rc;
+    return fill_equilibrium(h, 0.0f, index <= 8 ? (int)index : 9);
+}
+
+int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
+{
+    CKH(h);
+    if (npairs == 0) return BLBM_OK;
+    if (!pairs) return fail(BLBM_EINVAL, "pairs is null");
+    // keep, per location, the last pair (sequential scatter semantics), then upload what touches this slab
+    std::vector<std::pair<uint64_t, uint64_t>> idx;  // (location, position)
+    try {
+        idx.reserve(npairs);
+    } catch (...) {
+        return fail(BLBM_ENOMEM, "out of host memory");
+    }
+    const uint64_t total = (uint64_t)h->W * h->Hg;
+    const uint64_t lo = (h->row0 >= 2 ? h->row0 - 2 : 0) * (uint64_t)h->W;
+    const uint64_t hi = std::min<uint64_t>(h->Hg, h->row1 + 2) * (uint64_t)h->W;
+    for (size_t p = 0; p < npairs; p++) {
+        const uint64_t loc = pairs[2 * p];
+        if (loc >= total || loc < lo || loc >= hi) continue;
+        idx.emplace_back(loc, (uint64_t)p);
+    }
+    std::sort(idx.begin(), idx.end());
+    std::vector<uint64_t> uniq;
+    uniq.reserve(idx.size() * 2);
+    for (size_t q = 0; q < idx.size(); q++) {
+        if (q + 1 < idx.size() && idx[q + 1].first == idx[q].first) continue;
+        uniq.push_back(idx[q].first);
+        uniq.push_back(pairs[2 * idx[q].second + 1]);
+    }
+    const size_t nu = uniq.size() / 2;
+    if (nu) {
+        if (h->d_pairs_cap < nu) {
+            if (h->d_pairs) {
+                CK(cudaStreamSynchronize(h->stream));
+                CK(cudaFree(h->d_pairs));
+                h->d_pairs = nullptr;
+                h->d_pairs_cap = 0;
+            }
+            const size_t cap = std::max<size_t>(nu, 4096);
+            cudaError_t e = cudaMalloc(&h->d_pairs, cap * 2 * sizeof(uint64_t));
+            if (e != cudaSuccess) return fail(BLBM_ENOMEM, "cudaMalloc for paint list failed");
+            h->d_pairs_cap = cap;
+        }
+        CK(cudaMemcpyAsync(h->d_pairs, uniq.data(), nu * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        CK(launch_mask_scatter(h->mask, geom(h), h->d_pairs, nu, h->stream));
+        h->launches++;
+        CK(cudaStreamSynchronize(h->stream));  // uniq is pageable host memory owned by this frame
+    }
+    // every slab rebuilds, whether or not a point landed here: keeps launch sequences identical
+    return rebuild_class(h);
+}
+
+int blbm_draw_points(blbm_t *h, const uint32_t *pairs, size_t npairs)
+{
+    if (!h) return fail(BLBM_EINVAL, "null handle");
+    if (npairs == 0) return BLBM_OK;
+    if (!pairs) return fail(BLBM_EINVAL, "pairs is null");
+    std::vector<uint64_t> wide;
+    try {
+        wide.resize(npairs * 2);
+    } catch (...) {
+        return fail(BLBM_ENOMEM, "out of host memory");
+    }
+    for (size_t q = 0; q < npairs * 2; q++) wide[q] = pairs[q];
+    return blbm_draw_points64(h, wide.data(), npairs);
+}
+
+int blbm_reset_barrier(blbm_t *h)
+{
+    CKH(h);
+    CK(launch_mask_init(h->mask, geom(h), h->stream));
+    h->launches++;
+    return rebuild_class(h);
+}
+
+uint64_t blbm_get_compute_num(const blbm_t *h) { return h ? h->step : 0; }
+uint64_t blbm_get_frame_num(const blbm_t *h) { return h ? h->frame : 0; }
+
+static int copy_plane_to_host(blbm *h, const float *plane, float *dst)
+{
+    CK(cudaMemcpy2DAsync(dst, (size_t)h->W * sizeof(float), plane + row_off(0, h->P), (size_t)h->P * sizeof(float),
+                         (size_t)h->W * sizeof(float), h->rows, cudaMemcpyDeviceToHost, h->stream));
+    return BLBM_OK;
+}
+
+static float *population_plane(blbm *h, int buffer, int k)
+{
+    static const int dir_of_pop[9] = {D_NW, D_N, D_NE, D_W, -1, D_E, D_SW, D_S, D_SE};
+    if (k == BLBM_REST) return h->R;
+    if (buffer < 0) buffer = (int)(h->step % 2);
+    return h->f[buffer][dir_of_pop[k]];
+}
+
+int blbm_read_population(blbm_t *h, int buffer, int k, float *dst)
+{
+    CKH(h);
+    if (!dst || k < 0 || k > 8 || buffer < -1 || buffer > 1) return fail(BLBM_EINVAL, "bad argument");
+    int rc = materialise(h);
+    if (rc) return rc;
+    rc = copy_plane_to_host(h, population_plane(h, buffer, k), dst);
+    if (rc) return rc;
+    return sync_stream(h);
+}
+
+int blbm_write_population(blbm_t *h, int buffer, int k, const float *src)
+{
+    CKH(h);
+    if (!src || k < 0 || k > 8 || buffer < -1 || buffer > 1) return fail(BLBM_EINVAL, "bad argument");
+    int rc = materialise(h);
+    if (rc) return rc;
+    float *plane = population_plane(h, buffer, k);
+    CK(cudaMemcpy2DAsync(plane + row_off(0, h->P), (size_t)h->P * sizeof(float), src, (size_t)h->W * sizeof(float),
+                         (size_t)h->W * sizeof(float), h->rows, cudaMemcpyHostToDevice, h->stream));
+    h->halo_dirty = true;
+    return sync_stream(h);
+}
+
+int blbm_read_moments(blbm_t *h, float *mx, float *my, float *rho)
+{
+    CKH(h);
+    int rc;
+    if (mx && (rc = copy_plane_to_host(h, h->mx, mx))) return rc;
+    if (my && (rc = copy_plane_to_host(h, h->my, my))) return rc;
+    if (rho && (rc = copy_plane_to_host(h, h->rho, rho))) return rc;
+    return sync_stream(h);
+}
+
+int blbm_read_output(blbm_t *h, float *dst)
+{
+    CKH(h);
+    if (!dst) return fail(BLBM_EINVAL, "dst is null");
+    int rc = copy_plane_to_host(h, h->out, dst);
+    if (rc) return rc;
+    return sync_stream(h);
+}
+
+int blbm_read_output_async(blbm_t *h, float *pinned_dst)
+{
+    CKH(h);
+    if (!pinned_dst) return fail(BLBM_EINVAL, "dst is null");
+    return copy_plane_to_host(h, h->out, pinned_dst);
+}
+
+int blbm_synchronize(blbm_t *h)
+{
+    CKH(h);
+    return sync_stream(h);
+}
+
+int blbm_read_barrier(blbm_t *h, uint32_t *dst)
+{
+    CKH(h);
+    if (!dst) return fail(BLBM_EINVAL, "dst is null");
+    std::vector<uint8_t> tmp;
+    try {
+        tmp.resize((size_t)h->rows * h->W);
+    } catch (...) {
+        return fail(BLBM_ENOMEM, "out of host memory");
+    }
+    CK(cudaMemcpy2DAsync(tmp.data(), h->W, h->mask + mask_row_off(0, h->P), h->P, h->W, h->rows,
+                         cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_stream(h);
+    if (rc) return rc;
+    for (size_t q = 0; q < tmp.size(); q++) dst[q] = tmp[q];
+    return BLBM_OK;
+}
+
+int blbm_read_cell_class(blbm_t *h, uint16_t *dst)
+{
+    CKH(h);
+    if (!dst) return fail(BLBM_EINVAL, "dst is null");
+    const uint16_t *c = h->cls[h->cls_pending ? (h->cls_cur ^ 1) : h->cls_cur];  // class of the current mask
+    CK(cudaMemcpy2DAsync(dst, (size_t)h->W * 2, c + row_off(0, h->P), (size_t)h->P * 2, (size_t)h->W * 2, h->rows,
+                         cudaMemcpyDeviceToHost, h->stream));
+    return sync_stream(h);
+}
+
+int blbm_reduce_moments(blbm_t *h, double *sum_rho, double *sum_mx, double *sum_my, float *max_abs_output)
+{
+    CKH(h);
+    CK(launch_reduce(h->mx, h->my, h->rho, h->out, geom(h), h->red_sums, h->red_max, h->stream));
+    h->launches++;
+    double s[3];
+    float m;
+    CK(cudaMemcpyAsync(s, h->red_sums, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&m, h->red_max, sizeof(m), cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_stream(h);
+    if (rc) return rc;
+    if (sum_rho) *sum_rho = s[0];
+    if (sum_mx) *sum_mx = s[1];
+    if (sum_my) *sum_my = s[2];
+    if (max_abs_output) *max_abs_output = m;
+    return BLBM_OK;
+}
+
+int blbm_get_geometry(const blbm_t *h, uint32_t *w, uint64_t *h_global, uint64_t *row_begin, uint64_t *row_end,
+                      int *device)
+{
+    if (!h) return fail(BLBM_EINVAL, "null handle");
+    if (w) *w = h->W;
+    if (h_global) *h_global = h->Hg;
+    if (row_begin) *row_begin = h->row0;
+    if (row_end) *row_end = h->row1;
+    if (device) *device = h->device;
+    return BLBM_OK;
+}
+
+int blbm_export_peer(blbm_t *h, void *blob)
+{
+    CKH(h);
+    if (!blob) return fail(BLBM_EINVAL, "blob is null");
+    PeerBlob b;
+    fill_blob(h, &b);
+    CK(cudaIpcGetMemHandle(&b.ipc, h->pool));
+    memset(blob, 0, BLBM_PEER_HANDLE_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return BLBM_OK;
+}
+
+int blbm_link_peer(blbm_t *h, int side, const void *blob)
+{
+    CKH(h);
+    if (!blob || (side != 0 && side != 1)) return fail(BLBM_EINVAL, "bad argument");
+    PeerBlob b;
+    memcpy(&b, blob, sizeof(b));
+    if (b.magic != PEER_MAGIC) return fail(BLBM_EINVAL, "bad peer blob");
+    char *base = nullptr;
+    bool opened = false;
+    if (b.pid == (int32_t)getpid()) {
+        base = reinterpret_cast<char *>((uintptr_t)b.local_ptr);
+        if (b.device != h->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(BLBM_EPEER, "cudaDeviceEnablePeerAccess(%d) failed: %s", b.device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    } else {
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(BLBM_EPEER, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+        base = static_cast<char *>(p);
+        opened = true;
+    }
+    int rc = attach_peer(h, side, b, base, opened);
+    if (rc != BLBM_OK && opened) cudaIpcCloseMemHandle(base);
+    if (rc) return rc;
+    h->halo_dirty = true;
+    return BLBM_OK;
+}
+
+int blbm_link_local(blbm_t *upper, blbm_t *lower)
+{
+    if (!upper || !lower) return fail(BLBM_EINVAL, "null handle");
+    unsigned char bu[BLBM_PEER_HANDLE_BYTES], bl[BLBM_PEER_HANDLE_BYTES];
+    PeerBlob b;
+    fill_blob(upper, &b);
+    memset(bu, 0, sizeof(bu));
+    memcpy(bu, &b, sizeof(b));
+    fill_blob(lower, &b);
+    memset(bl, 0, sizeof(bl));
+    memcpy(bl, &b, sizeof(b));
+    int rc = blbm_link_peer(upper, 1, bl);
+    if (rc) return rc;
+    return blbm_link_peer(lower, 0, bu);
+}
+
+int blbm_exchange_halos(blbm_t *h)
+{
+    CKH(h);
+    if (!any_peer(h)) return BLBM_OK;
+    int rc = materialise(h);
+    if (rc) return rc;
+    return push_all_halos(h);
+}
+
+int blbm_set_kernel(blbm_t *h, int kernel)
+{
+    if (!h) return fail(BLBM_EINVAL, "null handle");
+    switch (kernel) {
+    case BLBM_KERNEL_AUTO: h->kernel = BLBM_KERNEL_VEC4; break;
+    case BLBM_KERNEL_SCALAR:
+    case BLBM_KERNEL_VEC4: h->kernel = kernel; break;
+    default: return fail(BLBM_EINVAL, "kernel %d not available", kernel);
+    }
+    return BLBM_OK;
+}
+
+int blbm_get_kernel(const blbm_t *h) { return h ? h->kernel : BLBM_EINVAL; }
+uint64_t blbm_get_launch_count(const blbm_t *h) { return h ? h->launches : 0; }
+uint64_t blbm_get_device_bytes(const blbm_t *h) { return h ? h->pool_bytes : 0; }
+
+}  // extern "C"

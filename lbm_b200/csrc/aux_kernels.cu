@@ -1,0 +1,358 @@
+// aux_kernels.cu — everything around the step kernel: initial conditions, barrier mask and cell
+// classification, the summary-stat kernels that feed the renderer, reductions, and the
+// neighbour-slab flag handshake.  All rare or cheap relative to the step kernel.
+#include "blbm_internal.cuh"
+
+namespace blbmk {
+
+// ---- uniform fill of row ranges (set_equil broadcast, lbm.rs:611-643 / :1078-1081) ---------------
+struct FillArgs {
+    float *plane[20];
+    float value[20];
+    int n;
+    uint32_t W, P, row_begin, row_end;
+};
+
+__global__ void fill_rows_kernel(const FillArgs a)
+{
+    const uint32_t rows = a.row_end - a.row_begin;
+    const size_t per_plane = (size_t)rows * a.W;
+    const size_t total = per_plane * a.n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t / per_plane);
+        const size_t rem = t - (size_t)k * per_plane;
+        const uint32_t r = (uint32_t)(rem / a.W);
+        const uint32_t x = (uint32_t)(rem - (size_t)r * a.W);
+        a.plane[k][(size_t)(a.row_begin + r) * a.P + x] = a.value[k];
+    }
+}
+
+cudaError_t launch_fill_rows(float *const *planes, const float *values, int nplanes, uint32_t W, uint32_t P,
+                             uint32_t dev_row_begin, uint32_t dev_row_end, cudaStream_t st)
+{
+    if (dev_row_end <= dev_row_begin || nplanes <= 0) return cudaSuccess;
+    if (nplanes > 20) return cudaErrorInvalidValue;
+    FillArgs a;
+    a.n = nplanes;
+    for (int k = 0; k < nplanes; k++) {
+        a.plane[k] = planes[k];
+        a.value[k] = values[k];
+    }
+    a.W = W;
+    a.P = P;
+    a.row_begin = dev_row_begin;
+    a.row_end = dev_row_end;
+    fill_rows_kernel<<<148 * 8, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- barrier mask --------------------------------------------------------------------------------
+// init_barrier, lbm.rs:595-605: rows 0 and H-1 are wall, everything else fluid.  The mask plane keeps
+// two halo rows on each side; rows outside the lattice stay 0 (out-of-range reads return 0).
+__global__ void mask_init_kernel(uint8_t *mask, const SlabGeom g)
+{
+    const size_t total = (size_t)(g.rows + 4) * g.P;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t dr = (uint32_t)(t / g.P);
+        const uint32_t x = (uint32_t)(t - (size_t)dr * g.P);
+        const int64_t gy = (int64_t)g.row0 + (int64_t)dr - 2;
+        uint8_t v = 0;
+        if (x < g.W && gy >= 0 && gy < (int64_t)g.Hg && (gy == 0 || gy == (int64_t)g.Hg - 1)) v = 1;
+        mask[t] = v;
+    }
+}
+
+cudaError_t launch_mask_init(uint8_t *mask, const SlabGeom &g, cudaStream_t st)
+{
+    mask_init_kernel<<<148 * 4, 256, 0, st>>>(mask, g);
+    return cudaGetLastError();
+}
+
+// barrier_draw.wgsl:11-18: barrier[location] = value.  pairs are (global location, value), already
+// de-duplicated on the host (last writer wins); locations outside this slab's mask window are ignored.
+__global__ void mask_scatter_kernel(uint8_t *mask, const SlabGeom g, const uint64_t *pairs, size_t npairs)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npairs;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t loc = pairs[2 * t], val = pairs[2 * t + 1];
+        const uint64_t gy = loc / g.W;
+        const uint32_t x = (uint32_t)(loc - gy * g.W);
+        if (gy >= g.Hg) continue;
+        const int64_t lr = (int64_t)gy - (int64_t)g.row0;  // local row, halo rows are -2,-1 and rows,rows+1
+        if (lr < -2 || lr >= (int64_t)g.rows + 2) continue;
+        mask[mask_row_off(lr, g.P) + x] = (val == 1u) ? 1 : 0;
+    }
+}
+
+cudaError_t launch_mask_scatter(uint8_t *mask, const SlabGeom &g, const uint64_t *pairs, size_t npairs,
+                                cudaStream_t st)
+{
+    if (npairs == 0) return cudaSuccess;
+    size_t nb = (npairs + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    mask_scatter_kernel<<<(unsigned)nb, 256, 0, st>>>(mask, g, pairs, npairs);
+    return cudaGetLastError();
+}
+
+// Cell classification from the mask: which cells the stream passes skip (e_w_stream.wgsl:31-45) and, per
+// moving population, whether the cell it is pulled from is a barrier (e_w_stream.wgsl:51-62), with the
+// reference's flat-index neighbours (column W-1's east side is column 0 of the next row) and
+// out-of-range reads returning 0.
+__device__ __forceinline__ uint32_t mask_at(const uint8_t *mask, const SlabGeom &g, int64_t gx, int64_t gy)
+{
+    if (gx == (int64_t)g.W) {
+        gx = 0;
+        gy += 1;
+    } else if (gx < 0) {
+        gx = (int64_t)g.W - 1;
+        gy -= 1;
+    }
+    if (gy < 0 || gy >= (int64_t)g.Hg) return 0;
+    const int64_t lr = gy - (int64_t)g.row0;
+    if (lr < -2 || lr >= (int64_t)g.rows + 2) return 0;  // cannot happen for owned cells
+    return mask[mask_row_off(lr, g.P) + (size_t)gx];
+}
+
+__global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const SlabGeom g)
+{
+    const size_t total = (size_t)g.rows * g.P;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / g.P);
+        const uint32_t x = (uint32_t)(t - (size_t)r * g.P);
+        uint16_t c = 0;
+        if (x < g.W) {
+            const int64_t gy = (int64_t)g.row0 + r;
+            const bool bar = mask[mask_row_off(r, g.P) + x] == 1;
+            if (bar) c |= CLS_BARRIER;
+            if (bar || x == 0 || gy >= (int64_t)g.Hg - 1) c |= CLS_SKIP;
+#pragma unroll
+            for (int d = 0; d < 8; d++)
+                if (mask_at(mask, g, (int64_t)x - dir_dx(d), gy - dir_dy(d)) == 1) c |= cls_upstream_bit(d);
+        }
+        cls[row_off(r, g.P) + x] = c;
+    }
+}
+
+cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, cudaStream_t st)
+{
+    build_class_kernel<<<148 * 8, 256, 0, st>>>(cls, mask, g);
+    return cudaGetLastError();
+}
+
+// ---- moments without the rest term (reset_to_equilibrium / custom_speed, lbm.rs:1082-1087) ----------
+struct MomArgs {
+    const float *f[8];
+    float *mx, *my, *rho;
+    uint32_t W, P, row_begin, row_end;
+};
+
+__global__ void precollision_moments_kernel(const MomArgs a)
+{
+    const size_t total = (size_t)(a.row_end - a.row_begin) * a.W;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / a.W);
+        const uint32_t x = (uint32_t)(t - (size_t)r * a.W);
+        const size_t i = (size_t)(a.row_begin + r) * a.P + x;
+        float f[8], mx, my, rho;
+#pragma unroll
+        for (int d = 0; d < 8; d++) f[d] = a.f[d][i];
+        precollision_moments(f, mx, my, rho);
+        a.mx[i] = mx;
+        a.my[i] = my;
+        a.rho[i] = rho;
+    }
+}
+
+cudaError_t launch_precollision_moments(const float *const *f8, float *mx, float *my, float *rho, uint32_t W,
+                                        uint32_t P, uint32_t dev_row_begin, uint32_t dev_row_end,
+                                        cudaStream_t st)
+{
+    if (dev_row_end <= dev_row_begin) return cudaSuccess;
+    MomArgs a;
+    for (int d = 0; d < 8; d++) a.f[d] = f8[d];
+    a.mx = mx;
+    a.my = my;
+    a.rho = rho;
+    a.W = W;
+    a.P = P;
+    a.row_begin = dev_row_begin;
+    a.row_end = dev_row_end;
+    precollision_moments_kernel<<<148 * 8, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- summary statistics, summary_stats/{curl,ux,uy,rho,speed}.wgsl ------------------------------------
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+template <int STAT>
+__global__ void summary_kernel(const float *__restrict__ mx, const float *__restrict__ my,
+                               const float *__restrict__ rho, float *__restrict__ out, const SlabGeom g)
+{
+    const size_t total = (size_t)g.rows * g.W;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / g.W);
+        const uint32_t x = (uint32_t)(t - (size_t)r * g.W);
+        const size_t i = row_off(r, g.P) + x;
+        if (STAT == 0) {
+            // curl.wgsl:37-49 — skips column 0 and rows >= H-1 (their output keeps its old value);
+            // index+1 at column W-1 is column 0 of the next row (flat index)
+            if (x == 0) continue;
+            if (g.row0 + r >= g.Hg - 1) continue;
+            const float a = (x + 1 < g.W) ? my[i + 1] : my[i - x + g.P];
+            const float b = my[i - 1];
+            const float c = mx[i - g.P];
+            const float d = mx[i + g.P];
+            out[i] = __fdiv_rn(__fmul_rn(10.0f, __fadd_rn(__fsub_rn(__fsub_rn(a, b), c), d)), rho[i]);
+        } else if (STAT == 1) {
+            out[i] = mx[i];
+        } else if (STAT == 2) {
+            out[i] = my[i];
+        } else if (STAT == 3) {
+            out[i] = __fsub_rn(__fmul_rn(4.0f, clamp01(__fmul_rn(0.15f, rho[i]))), 0.5f);
+        } else {
+            const float s2 = __fadd_rn(__fmul_rn(mx[i], mx[i]), __fmul_rn(my[i], my[i]));
+            out[i] = __fsub_rn(clamp01(__fmul_rn(5.0f, __fsqrt_rn(s2))), 0.5f);
+        }
+    }
+}
+
+cudaError_t launch_summary(int stat, const float *mx, const float *my, const float *rho, float *out,
+                           const SlabGeom &g, cudaStream_t st)
+{
+    const size_t total = (size_t)g.rows * g.W;
+    size_t nb = (total + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb == 0) return cudaSuccess;
+    const unsigned b = (unsigned)nb;
+    switch (stat) {
+    case 0: summary_kernel<0><<<b, 256, 0, st>>>(mx, my, rho, out, g); break;
+    case 1: summary_kernel<1><<<b, 256, 0, st>>>(mx, my, rho, out, g); break;
+    case 2: summary_kernel<2><<<b, 256, 0, st>>>(mx, my, rho, out, g); break;
+    case 3: summary_kernel<3><<<b, 256, 0, st>>>(mx, my, rho, out, g); break;
+    case 4: summary_kernel<4><<<b, 256, 0, st>>>(mx, my, rho, out, g); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ---- global reductions: warp shuffles, one atomic per block ---------------------------------------
+__global__ void reduce_kernel(const float *__restrict__ mx, const float *__restrict__ my,
+                              const float *__restrict__ rho, const float *__restrict__ out, const SlabGeom g,
+                              double *sums3, float *maxabs)
+{
+    double s_rho = 0.0, s_mx = 0.0, s_my = 0.0;
+    float m = 0.0f;
+    const size_t total = (size_t)g.rows * g.W;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / g.W);
+        const uint32_t x = (uint32_t)(t - (size_t)r * g.W);
+        const size_t i = row_off(r, g.P) + x;
+        s_rho += (double)rho[i];
+        s_mx += (double)mx[i];
+        s_my += (double)my[i];
+        m = fmaxf(m, fabsf(out[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_rho += __shfl_xor_sync(0xffffffffu, s_rho, o);
+        s_mx += __shfl_xor_sync(0xffffffffu, s_mx, o);
+        s_my += __shfl_xor_sync(0xffffffffu, s_my, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    __shared__ double sh[3][8];
+    __shared__ float shm[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[0][warp] = s_rho;
+        sh[1][warp] = s_mx;
+        sh[2][warp] = s_my;
+        shm[warp] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        float mm = 0.f;
+        for (int w = 0; w < 8; w++) {
+            a += sh[0][w];
+            b += sh[1][w];
+            c += sh[2][w];
+            mm = fmaxf(mm, shm[w]);
+        }
+        atomicAdd(&sums3[0], a);
+        atomicAdd(&sums3[1], b);
+        atomicAdd(&sums3[2], c);
+        atomicMax(reinterpret_cast<int *>(maxabs), __float_as_int(mm));  // non-negative floats order as ints
+    }
+}
+
+cudaError_t launch_reduce(const float *mx, const float *my, const float *rho, const float *out,
+                          const SlabGeom &g, double *sums3, float *maxabs, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(sums3, 0, 3 * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(maxabs, 0, sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    reduce_kernel<<<148 * 4, 256, 0, st>>>(mx, my, rho, out, g, sums3, maxabs);
+    return cudaGetLastError();
+}
+
+// ---- neighbour handshake: one 64-bit epoch word per face, in the receiver's memory ------------------
+__global__ void signal_kernel(unsigned long long *remote_up, unsigned long long *remote_dn,
+                              unsigned long long epoch)
+{
+    // everything the preceding kernels on this stream stored into the neighbours' halo rows is ordered
+    // before the flag by the kernel boundary plus this system-scope fence
+    __threadfence_system();
+    if (remote_up) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_up), "l"(epoch) : "memory");
+    if (remote_dn) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_dn), "l"(epoch) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void wait_kernel(const unsigned long long *from_up, const unsigned long long *from_dn,
+                            unsigned long long epoch, int *err_flag, unsigned long long timeout_ns)
+{
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (*reinterpret_cast<volatile int *>(err_flag)) return;  // a previous wait already gave up
+    for (;;) {
+        const bool up_ok = !from_up || ld_acquire_sys(from_up) >= epoch;
+        const bool dn_ok = !from_dn || ld_acquire_sys(from_dn) >= epoch;
+        if (up_ok && dn_ok) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {  // never hang the GPU on a dead neighbour: flag and carry on
+            *err_flag = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+cudaError_t launch_signal(unsigned long long *remote_up, unsigned long long *remote_dn,
+                          unsigned long long epoch, cudaStream_t st)
+{
+    signal_kernel<<<1, 1, 0, st>>>(remote_up, remote_dn, epoch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wait(const unsigned long long *from_up, const unsigned long long *from_dn,
+                        unsigned long long epoch, int *err_flag, unsigned long long timeout_ns,
+                        cudaStream_t st)
+{
+    wait_kernel<<<1, 1, 0, st>>>(from_up, from_dn, epoch, err_flag, timeout_ns);
+    return cudaGetLastError();
+}
+
+}  // namespace blbmk

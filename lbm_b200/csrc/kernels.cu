@@ -1,0 +1,288 @@
+// kernels.cu — the fused stream+collide step kernels (scalar and 128-bit vectorised) for sm_100a.
+//
+// What one launch computes ("pull-T" formulation).  Between steps the device
+// holds T_{k-1} = the post-collision populations of step k-1 in buffer X = (k-1)%2 at EVERY cell — the
+// same thing the reference's collide passes leave in place (collision/*.wgsl run over all cells with
+// no mask test).  Step k of the reference is
+//     stream  (stream/*.wgsl, 4 passes)   X -> Y at active cells only; skipped cells keep Y's old data
+//     collide (pre_collision/*.wgsl + collision/*.wgsl, 4 passes) in place on Y, every cell
+// and this kernel does both in one pass: an active cell gathers S_k from X (pull streaming with
+// half-way bounce-back, e_w_stream.wgsl:51-62 etc.), a skipped cell (barrier | x==0 | y>=H-1,
+// e_w_stream.wgsl:31-45) re-reads its own stale copy from Y, then every cell is collided and written
+// to Y.  9 fp32 loads + 9 fp32 stores per cell = 72 B, the algorithmic minimum of a two-lattice D2Q9.
+#include "blbm_internal.cuh"
+
+namespace blbmk {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void stg4(float *p, const float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// Offset of the cell population d is pulled from, for the cell at (x, device-row offset `i`).
+// Column W-1 follows the reference's flat indexing: i+1 is (0, y+1)  (SURVEY.md section 8 a-4).
+__device__ __forceinline__ size_t pull_src(const size_t i, const uint32_t x, const int d, const uint32_t W,
+                                           const uint32_t P)
+{
+    const int dx = dir_dx(d), dy = dir_dy(d);
+    if (dx < 0 && x == W - 1) {
+        // source = flat index i + 1 - dy*W  ->  column 0 of row (y + 1 - dy)
+        return i - x + (size_t)((1 - dy)) * P;
+    }
+    return (size_t)((ptrdiff_t)i - dx - (ptrdiff_t)dy * (ptrdiff_t)P);
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar kernel: one cell per thread.  Used for the collide-only and stream-only passes, for tiny
+// lattices and as the in-GPU cross-check of the vectorised kernels.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool MOM>
+__global__ void __launch_bounds__(128) step_scalar_kernel(const StepParams p)
+{
+    const uint32_t nbx = (p.W + 127u) / 128u;
+    const uint32_t bx = blockIdx.x % nbx;
+    const uint32_t r = blockIdx.x / nbx;  // owned row index
+    const uint32_t x = bx * 128u + threadIdx.x;
+    if (x >= p.W) return;
+    const size_t i = row_off(r, p.P) + x;
+    const uint16_t c = p.cls[i];
+    const bool skipped = (c & CLS_SKIP) != 0;
+
+    float f[8];
+    if (MODE == MODE_STREAM_ONLY && skipped) return;  // destination untouched, like the WGSL early return
+    if (MODE == MODE_COLLIDE_ONLY || (MODE == MODE_FUSED && skipped)) {
+#pragma unroll
+        for (int d = 0; d < 8; d++) f[d] = p.Y[d][i];
+    } else {
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            if (c & cls_upstream_bit(d))
+                f[d] = p.X[dir_opp(d)][i];  // half-way bounce-back
+            else
+                f[d] = p.X[d][pull_src(i, x, d, p.W, p.P)];
+        }
+    }
+    if (MODE == MODE_STREAM_ONLY) {
+#pragma unroll
+        for (int d = 0; d < 8; d++) p.Y[d][i] = f[d];
+        return;
+    }
+
+    float rest = p.R[i], mx, my, rho;
+    collide_cell(f, rest, p.omega, mx, my, rho);
+    p.R[i] = rest;
+#pragma unroll
+    for (int d = 0; d < 8; d++) p.Y[d][i] = f[d];
+    if (MOM) {
+        p.mx[i] = mx;
+        p.my[i] = my;
+        p.rho[i] = rho;
+    }
+    // mirror the cells a neighbouring slab gathers from into its halo rows (NVLink stores)
+    if (r == 0 && p.push.up_n) {
+        p.push.up_n[x] = f[D_N];
+        p.push.up_ne[x] = f[D_NE];
+        p.push.up_nw[x] = f[D_NW];
+        if (x == 0) p.push.up_w[0] = f[D_W];
+        if (MOM) {
+            p.push.up_mx[x] = mx;
+            p.push.up_my[x] = my;
+        }
+    }
+    if (r == 1 && x == 0 && p.push.up_nw2) p.push.up_nw2[0] = f[D_NW];
+    if (r == p.rows - 1 && p.push.dn_s) {
+        p.push.dn_s[x] = f[D_S];
+        p.push.dn_se[x] = f[D_SE];
+        p.push.dn_sw[x] = f[D_SW];
+        if (MOM) {
+            p.push.dn_mx[x] = mx;
+            p.push.dn_my[x] = my;
+        }
+    }
+}
+
+cudaError_t launch_step_scalar(const StepParams &p, int mode, bool mom, cudaStream_t st)
+{
+    const uint32_t nbx = (p.W + 127u) / 128u;
+    const uint64_t nblocks = (uint64_t)nbx * p.rows;
+    if (nblocks == 0 || nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)nblocks), block(128);
+    if (mode == MODE_FUSED) {
+        if (mom) step_scalar_kernel<MODE_FUSED, true><<<grid, block, 0, st>>>(p);
+        else step_scalar_kernel<MODE_FUSED, false><<<grid, block, 0, st>>>(p);
+    } else if (mode == MODE_COLLIDE_ONLY) {
+        if (mom) step_scalar_kernel<MODE_COLLIDE_ONLY, true><<<grid, block, 0, st>>>(p);
+        else step_scalar_kernel<MODE_COLLIDE_ONLY, false><<<grid, block, 0, st>>>(p);
+    } else {
+        step_scalar_kernel<MODE_STREAM_ONLY, false><<<grid, block, 0, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// vec4 kernel: four consecutive cells per thread, every global access an aligned 128-bit transaction.
+// The six populations that move in x are realigned by one float through warp shuffles; the lane at
+// the warp edge fetches the single missing float itself.  A block is 32 x 8 threads = 128 x 8 cells.
+// Cells that need anything but a plain pull (class word != 0, column W-1, ragged row end) take a
+// per-cell fix-up path after the vector loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int V4_ROWS = 8;
+
+template <bool MOM>
+__global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParams p)
+{
+    const uint32_t nbx = (p.P + 127u) / 128u;
+    const uint32_t bx = blockIdx.x % nbx;
+    const uint32_t r = (blockIdx.x / nbx) * V4_ROWS + threadIdx.y;
+    if (r >= p.rows) return;  // whole warps leave together (a warp is one row)
+    const uint32_t lane = threadIdx.x;
+    const uint32_t x4 = bx * 128u + lane * 4u;
+    const bool valid = x4 < p.W;  // P is a multiple of 32, so x4 + 3 < P always
+    const uint32_t P = p.P, W = p.W;
+    const size_t i = row_off(r, P) + x4;
+    const unsigned FULL = 0xffffffffu;
+
+    float g[4][8];  // [cell][direction], gathered pre-collision state
+    ushort4 c4 = make_ushort4(0, 0, 0, 0);
+    float4 vn, vs, ve, vw, vne, vnw, vse, vsw, vr;
+    vn = vs = ve = vw = vne = vnw = vse = vsw = vr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
+        vn = ldg4(p.X[D_N] + i + P);
+        vne = ldg4(p.X[D_NE] + i + P);
+        vnw = ldg4(p.X[D_NW] + i + P);
+        ve = ldg4(p.X[D_E] + i);
+        vw = ldg4(p.X[D_W] + i);
+        vs = ldg4(p.X[D_S] + i - P);
+        vse = ldg4(p.X[D_SE] + i - P);
+        vsw = ldg4(p.X[D_SW] + i - P);
+        vr = ldg4(p.R + i);
+    }
+    // element x4-1 of the east-moving populations, element x4+4 of the west-moving ones
+    float le = __shfl_up_sync(FULL, ve.w, 1), lne = __shfl_up_sync(FULL, vne.w, 1),
+          lse = __shfl_up_sync(FULL, vse.w, 1);
+    float rw = __shfl_down_sync(FULL, vw.x, 1), rnw = __shfl_down_sync(FULL, vnw.x, 1),
+          rsw = __shfl_down_sync(FULL, vsw.x, 1);
+    if (valid && lane == 0 && x4 != 0) {
+        le = p.X[D_E][i - 1];
+        lne = p.X[D_NE][i + P - 1];
+        lse = p.X[D_SE][i - P - 1];
+    }
+    if (valid && lane == 31) {  // x4+4 <= P: still inside the row pitch (or x=0 of the next row: unused)
+        rw = p.X[D_W][i + 4];
+        rnw = p.X[D_NW][i + P + 4];
+        rsw = p.X[D_SW][i - P + 4];
+    }
+    if (!valid) return;
+
+    g[0][D_N] = vn.x; g[1][D_N] = vn.y; g[2][D_N] = vn.z; g[3][D_N] = vn.w;
+    g[0][D_S] = vs.x; g[1][D_S] = vs.y; g[2][D_S] = vs.z; g[3][D_S] = vs.w;
+    g[0][D_E] = le; g[1][D_E] = ve.x; g[2][D_E] = ve.y; g[3][D_E] = ve.z;
+    g[0][D_NE] = lne; g[1][D_NE] = vne.x; g[2][D_NE] = vne.y; g[3][D_NE] = vne.z;
+    g[0][D_SE] = lse; g[1][D_SE] = vse.x; g[2][D_SE] = vse.y; g[3][D_SE] = vse.z;
+    g[0][D_W] = vw.y; g[1][D_W] = vw.z; g[2][D_W] = vw.w; g[3][D_W] = rw;
+    g[0][D_NW] = vnw.y; g[1][D_NW] = vnw.z; g[2][D_NW] = vnw.w; g[3][D_NW] = rnw;
+    g[0][D_SW] = vsw.y; g[1][D_SW] = vsw.z; g[2][D_SW] = vsw.w; g[3][D_SW] = rsw;
+
+    const uint32_t cany = (uint32_t)c4.x | c4.y | c4.z | c4.w;
+    const bool ragged = x4 + 4 > W - 1;  // group holds column W-1 or cells beyond the row end
+    if (cany != 0 || ragged) {
+        const uint16_t cc[4] = {c4.x, c4.y, c4.z, c4.w};
+        if (cany & CLS_SKIP) {
+            // skipped cells continue from their own stale copy in the destination buffer
+            float4 o[8];
+#pragma unroll
+            for (int d = 0; d < 8; d++) o[d] = ldg4(p.Y[d] + i);
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                if (cc[0] & CLS_SKIP) g[0][d] = o[d].x;
+                if (cc[1] & CLS_SKIP) g[1][d] = o[d].y;
+                if (cc[2] & CLS_SKIP) g[2][d] = o[d].z;
+                if (cc[3] & CLS_SKIP) g[3][d] = o[d].w;
+            }
+        }
+        if (cany & 0x3fcu) {
+            // half-way bounce-back: population d of a cell whose upstream neighbour is a barrier is the
+            // cell's own opposite population
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                const uint16_t bit = cls_upstream_bit(d);
+                if (cany & bit) {
+                    float4 own;
+                    if (dir_opp(d) == D_E) own = ve;
+                    else if (dir_opp(d) == D_W) own = vw;
+                    else own = ldg4(p.X[dir_opp(d)] + i);
+                    if ((cc[0] & (bit | CLS_SKIP)) == bit) g[0][d] = own.x;
+                    if ((cc[1] & (bit | CLS_SKIP)) == bit) g[1][d] = own.y;
+                    if ((cc[2] & (bit | CLS_SKIP)) == bit) g[2][d] = own.z;
+                    if ((cc[3] & (bit | CLS_SKIP)) == bit) g[3][d] = own.w;
+                }
+            }
+        }
+        if (ragged) {
+            const uint32_t j = W - 1 - x4;  // position of column W-1 inside the group (0..3), if present
+            if (j < 4 && !(cc[j] & CLS_SKIP)) {
+                const size_t ij = i + j;
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    if (dir_dx(d) < 0 && !(cc[j] & cls_upstream_bit(d))) {
+                        const float v = p.X[d][pull_src(ij, W - 1, d, W, P)];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (q == (int)j) g[q][d] = v;
+                    }
+                }
+            }
+        }
+    }
+
+    float rr[4] = {vr.x, vr.y, vr.z, vr.w};
+    float mx[4], my[4], rho[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], p.omega, mx[q], my[q], rho[q]);
+
+    // cells beyond the row end (ragged W) are padding: written, never read
+    stg4(p.R + i, make_float4(rr[0], rr[1], rr[2], rr[3]));
+#pragma unroll
+    for (int d = 0; d < 8; d++) stg4(p.Y[d] + i, make_float4(g[0][d], g[1][d], g[2][d], g[3][d]));
+    if (MOM) {
+        stg4(p.mx + i, make_float4(mx[0], mx[1], mx[2], mx[3]));
+        stg4(p.my + i, make_float4(my[0], my[1], my[2], my[3]));
+        stg4(p.rho + i, make_float4(rho[0], rho[1], rho[2], rho[3]));
+    }
+    if (r == 0 && p.push.up_n) {
+        stg4(p.push.up_n + x4, make_float4(g[0][D_N], g[1][D_N], g[2][D_N], g[3][D_N]));
+        stg4(p.push.up_ne + x4, make_float4(g[0][D_NE], g[1][D_NE], g[2][D_NE], g[3][D_NE]));
+        stg4(p.push.up_nw + x4, make_float4(g[0][D_NW], g[1][D_NW], g[2][D_NW], g[3][D_NW]));
+        if (x4 == 0) p.push.up_w[0] = g[0][D_W];
+        if (MOM) {
+            stg4(p.push.up_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stg4(p.push.up_my + x4, make_float4(my[0], my[1], my[2], my[3]));
+        }
+    }
+    if (r == 1 && x4 == 0 && p.push.up_nw2) p.push.up_nw2[0] = g[0][D_NW];
+    if (r == p.rows - 1 && p.push.dn_s) {
+        stg4(p.push.dn_s + x4, make_float4(g[0][D_S], g[1][D_S], g[2][D_S], g[3][D_S]));
+        stg4(p.push.dn_se + x4, make_float4(g[0][D_SE], g[1][D_SE], g[2][D_SE], g[3][D_SE]));
+        stg4(p.push.dn_sw + x4, make_float4(g[0][D_SW], g[1][D_SW], g[2][D_SW], g[3][D_SW]));
+        if (MOM) {
+            stg4(p.push.dn_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stg4(p.push.dn_my + x4, make_float4(my[0], my[1], my[2], my[3]));
+        }
+    }
+}
+
+cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, cudaStream_t st)
+{
+    if (mode != MODE_FUSED) return launch_step_scalar(p, mode, mom, st);
+    const uint32_t nbx = (p.P + 127u) / 128u;
+    const uint64_t nblocks = (uint64_t)nbx * ((p.rows + V4_ROWS - 1) / V4_ROWS);
+    if (nblocks == 0 || nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)nblocks), block(32, V4_ROWS);
+    if (mom) step_vec4_kernel<true><<<grid, block, 0, st>>>(p);
+    else step_vec4_kernel<false><<<grid, block, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace blbmk

@@ -1,0 +1,417 @@
+"""Host-side mirror of the reference's `pub struct LBM` over the C ABI (include/blbm.h).
+
+Method names, argument meaning and call order follow lbm-wgpu/src/lbm.rs so that code (and tests)
+written against the reference reads the same here:
+
+    reference (lbm.rs)                          here
+    LBM::new(&driver, omega, x, y)     :726     LBM(omega, x, y)
+    iterate(&driver, n)                :1065    iterate(n)
+    collide(&driver) / stream(&driver) :1118    collide() / stream()
+    rerender(&driver)                  :1104    rerender()
+    set_summary(stat)                  :1061    set_summary(stat)
+    draw_shape(&driver, &shape)        :1337    draw_shape(shape) / draw_points(pairs)
+    reset_barrier(&driver)             :1362    reset_barrier()
+    update_omega_buffer(&driver, w)    :1358    update_omega_buffer(w)
+    reset_to_equilibrium(&driver)      :1076    reset_to_equilibrium()
+    custom_speed(&driver, ux)          :1090    custom_speed(ux)
+    single_cell(&driver, index)        :1502    single_cell(index)
+    get_compute_num / get_frame_num    :1166    get_compute_num() / get_frame_num()
+
+`&Driver` disappears (the handle owns the CUDA device and stream).  Where the reference panics, these
+raise BlbmError.  Read-back methods are new: the reference never reads its buffers back.
+"""
+import ctypes as C
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+POP_NAMES = ("nw", "n", "ne", "w", "rest", "e", "sw", "s", "se")  # lbm.rs:632-640
+PEER_HANDLE_BYTES = 512
+
+
+class SummaryStat(enum.IntEnum):  # lbm.rs:10-16
+    Curl = 0
+    Ux = 1
+    Uy = 2
+    Rho = 3
+    Speed = 4
+
+
+class Kernel(enum.IntEnum):
+    Auto = 0
+    Scalar = 1
+    Vec4 = 2
+    Tma = 3
+
+
+class BlbmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"blbm error {code}: {msg}")
+        self.code = code
+
+
+def omega_from_viscosity(nu):
+    """lib.rs:183: omega = 1 / (3 nu + 0.5), evaluated in f32 like the reference."""
+    f = np.float32
+    return float(f(1.0) / (f(3.0) * f(nu) + f(0.5)))
+
+
+def library_path():
+    return os.environ.get("BLBM_LIBRARY", os.path.join(_HERE, "libblbm.so"))
+
+
+_lib = None
+
+# name -> (restype, argtypes); the single source of truth for the ctypes prototypes.  tests/test_abi.py
+# checks this table against include/blbm.h.
+_P, _U32, _U64, _I, _F, _SZ = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float, C.c_size_t
+PROTOTYPES = {
+    "blbm_last_error": (C.c_char_p, []),
+    "blbm_abi_version": (_I, []),
+    "blbm_device_count": (_I, []),
+    "blbm_create": (_I, [_U32, _U32, _F, _F, _I, C.POINTER(_P)]),
+    "blbm_create_slab": (_I, [_U32, _U64, _U64, _U64, _F, _F, _I, C.POINTER(_P)]),
+    "blbm_destroy": (_I, [_P]),
+    "blbm_iterate": (_I, [_P, _U32]),
+    "blbm_advance": (_I, [_P, _U32]),
+    "blbm_iterate_timed": (_I, [_P, _U32, C.POINTER(_F)]),
+    "blbm_collide": (_I, [_P]),
+    "blbm_stream": (_I, [_P]),
+    "blbm_set_summary": (_I, [_P, _I]),
+    "blbm_rerender": (_I, [_P]),
+    "blbm_compute_summary": (_I, [_P, _I]),
+    "blbm_set_omega": (_I, [_P, _F]),
+    "blbm_reset_to_equilibrium": (_I, [_P]),
+    "blbm_custom_speed": (_I, [_P, _F]),
+    "blbm_single_cell": (_I, [_P, _U32]),
+    "blbm_draw_points": (_I, [_P, _P, _SZ]),
+    "blbm_draw_points64": (_I, [_P, _P, _SZ]),
+    "blbm_reset_barrier": (_I, [_P]),
+    "blbm_get_compute_num": (_U64, [_P]),
+    "blbm_get_frame_num": (_U64, [_P]),
+    "blbm_read_population": (_I, [_P, _I, _I, _P]),
+    "blbm_write_population": (_I, [_P, _I, _I, _P]),
+    "blbm_read_moments": (_I, [_P, _P, _P, _P]),
+    "blbm_read_output": (_I, [_P, _P]),
+    "blbm_read_barrier": (_I, [_P, _P]),
+    "blbm_read_cell_class": (_I, [_P, _P]),
+    "blbm_read_output_async": (_I, [_P, _P]),
+    "blbm_synchronize": (_I, [_P]),
+    "blbm_reduce_moments": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(_F)]),
+    "blbm_get_geometry": (_I, [_P, C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64), C.POINTER(_U64),
+                               C.POINTER(_I)]),
+    "blbm_link_local": (_I, [_P, _P]),
+    "blbm_export_peer": (_I, [_P, _P]),
+    "blbm_link_peer": (_I, [_P, _I, _P]),
+    "blbm_exchange_halos": (_I, [_P]),
+    "blbm_set_kernel": (_I, [_P, _I]),
+    "blbm_get_kernel": (_I, [_P]),
+    "blbm_get_launch_count": (_U64, [_P]),
+    "blbm_get_device_bytes": (_U64, [_P]),
+}
+
+
+def load_library():
+    """dlopen libblbm.so and attach prototypes.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise BlbmError(-4, f"{path} not found: build it with `python -m lbm_b200.build` "
+                                "(there is no CPU fallback)")
+        lib = C.CDLL(path)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BlbmError(rc, load_library().blbm_last_error().decode(errors="replace"))
+
+
+class LBM:
+    """One slab of a D2Q9 BGK lattice on one B200 (the whole lattice unless `rows` is given)."""
+
+    def __init__(self, omega, x, y, inflow_ux=0.1, device=0, rows=None, kernel=Kernel.Auto):
+        self._L = load_library()
+        self._h = _P()
+        self.x, self.y = int(x), int(y)
+        if rows is None:
+            rows = (0, self.y)
+        self.row_begin, self.row_end = int(rows[0]), int(rows[1])
+        self.device = int(device)
+        _check(self._L.blbm_create_slab(self.x, self.y, self.row_begin, self.row_end, float(omega),
+                                        float(inflow_ux), self.device, C.byref(self._h)))
+        self.summary_stat = SummaryStat.Curl
+        if kernel != Kernel.Auto:
+            self.set_kernel(kernel)
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.blbm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def local_rows(self):
+        return self.row_end - self.row_begin
+
+    # -- the reference's methods
+    def iterate(self, compute_steps):
+        _check(self._L.blbm_iterate(self._h, int(compute_steps)))
+
+    def advance(self, compute_steps):
+        _check(self._L.blbm_advance(self._h, int(compute_steps)))
+
+    def iterate_timed(self, compute_steps):
+        ms = _F()
+        _check(self._L.blbm_iterate_timed(self._h, int(compute_steps), C.byref(ms)))
+        return ms.value
+
+    def collide(self):
+        _check(self._L.blbm_collide(self._h))
+
+    def stream(self):
+        _check(self._L.blbm_stream(self._h))
+
+    def rerender(self):
+        _check(self._L.blbm_rerender(self._h))
+
+    def set_summary(self, stat):
+        _check(self._L.blbm_set_summary(self._h, int(stat)))
+        self.summary_stat = SummaryStat(int(stat))
+
+    def compute_summary(self, stat):
+        _check(self._L.blbm_compute_summary(self._h, int(stat)))
+        self.summary_stat = SummaryStat(int(stat))
+
+    def update_omega_buffer(self, omega):
+        _check(self._L.blbm_set_omega(self._h, float(omega)))
+
+    def reset_to_equilibrium(self):
+        _check(self._L.blbm_reset_to_equilibrium(self._h))
+
+    def custom_speed(self, ux):
+        _check(self._L.blbm_custom_speed(self._h, float(ux)))
+
+    def single_cell(self, index):
+        _check(self._L.blbm_single_cell(self._h, int(index)))
+
+    def draw_points(self, pairs):
+        """pairs: flat [loc, val, loc, val, ...] (merge_shapes.rs:12-22) or an (n, 2) array."""
+        a = np.ascontiguousarray(pairs)
+        if a.dtype == np.uint64 or (a.size and int(a.max()) > 0xFFFFFFFF):
+            a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+            _check(self._L.blbm_draw_points64(self._h, a.ctypes.data, a.size // 2))
+        else:
+            a = np.ascontiguousarray(a, dtype=np.uint32).reshape(-1)
+            _check(self._L.blbm_draw_points(self._h, a.ctypes.data, a.size // 2))
+
+    def draw_shape(self, shape):
+        """shape: anything with get_points() -> iterable of (x, y, bool), like `trait Shape`
+        (barrier_shapes/mod.rs:11-19); flattened as get_points_vector does (merge_shapes.rs:12-22)."""
+        pts = list(shape.get_points())
+        if not pts:
+            return  # the reference's callers guard with is_empty() (lib.rs:147)
+        a = np.empty((len(pts), 2), np.uint64)
+        for q, (px, py, on) in enumerate(pts):
+            a[q, 0] = int(px) + int(py) * self.x
+            a[q, 1] = 1 if on else 0
+        self.draw_points(a)
+
+    def reset_barrier(self):
+        _check(self._L.blbm_reset_barrier(self._h))
+
+    def get_compute_num(self):
+        return int(self._L.blbm_get_compute_num(self._h))
+
+    def get_frame_num(self):
+        return int(self._L.blbm_get_frame_num(self._h))
+
+    # -- read-back (new)
+    def _shape(self):
+        return (self.local_rows, self.x)
+
+    def read_population(self, k, buffer=-1):
+        out = np.empty(self._shape(), np.float32)
+        _check(self._L.blbm_read_population(self._h, int(buffer), int(k), out.ctypes.data))
+        return out
+
+    def write_population(self, k, values, buffer=-1):
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        assert a.shape == self._shape()
+        _check(self._L.blbm_write_population(self._h, int(buffer), int(k), a.ctypes.data))
+
+    def read_moments(self):
+        mx, my, rho = (np.empty(self._shape(), np.float32) for _ in range(3))
+        _check(self._L.blbm_read_moments(self._h, mx.ctypes.data, my.ctypes.data, rho.ctypes.data))
+        return mx, my, rho
+
+    def read_output(self):
+        out = np.empty(self._shape(), np.float32)
+        _check(self._L.blbm_read_output(self._h, out.ctypes.data))
+        return out
+
+    def read_output_async(self, pinned_ptr):
+        _check(self._L.blbm_read_output_async(self._h, int(pinned_ptr)))
+
+    def read_barrier(self):
+        out = np.empty(self._shape(), np.uint32)
+        _check(self._L.blbm_read_barrier(self._h, out.ctypes.data))
+        return out
+
+    def read_cell_class(self):
+        out = np.empty(self._shape(), np.uint16)
+        _check(self._L.blbm_read_cell_class(self._h, out.ctypes.data))
+        return out
+
+    def reduce_moments(self):
+        a, b, c, m = C.c_double(), C.c_double(), C.c_double(), _F()
+        _check(self._L.blbm_reduce_moments(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(m)))
+        return a.value, b.value, c.value, m.value
+
+    def synchronize(self):
+        _check(self._L.blbm_synchronize(self._h))
+
+    # -- slabs
+    def export_peer(self):
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        _check(self._L.blbm_export_peer(self._h, buf))
+        return buf.raw
+
+    def link_peer(self, side, blob):
+        assert len(blob) == PEER_HANDLE_BYTES
+        _check(self._L.blbm_link_peer(self._h, int(side), C.c_char_p(blob)))
+
+    def exchange_halos(self):
+        _check(self._L.blbm_exchange_halos(self._h))
+
+    # -- tuning / measurement
+    def set_kernel(self, kernel):
+        _check(self._L.blbm_set_kernel(self._h, int(kernel)))
+
+    def get_kernel(self):
+        return Kernel(self._L.blbm_get_kernel(self._h))
+
+    def launch_count(self):
+        return int(self._L.blbm_get_launch_count(self._h))
+
+    def device_bytes(self):
+        return int(self._L.blbm_get_device_bytes(self._h))
+
+
+def slab_rows(y, nslabs):
+    """Row ranges of the y-slab decomposition: contiguous, sizes differ by at most one row."""
+    base, extra = divmod(int(y), int(nslabs))
+    out, r = [], 0
+    for s in range(nslabs):
+        n = base + (1 if s < extra else 0)
+        out.append((r, r + n))
+        r += n
+    return out
+
+
+class SlabGroup:
+    """A lattice split into y-slabs over several GPUs of THIS process, presented with the same methods
+    as `LBM`.  (One-process-per-GPU deployments link `LBM(rows=...)` slabs with export_peer/link_peer
+    instead; see bench.py.)"""
+
+    def __init__(self, omega, x, y, devices, inflow_ux=0.1, kernel=Kernel.Auto):
+        self.x, self.y = int(x), int(y)
+        self.ranges = slab_rows(y, len(devices))
+        self.slabs = [LBM(omega, x, y, inflow_ux, dev, rows=r, kernel=kernel)
+                      for dev, r in zip(devices, self.ranges)]
+        L = load_library()
+        for up, lo in zip(self.slabs[:-1], self.slabs[1:]):
+            _check(L.blbm_link_local(up._h, lo._h))
+
+    def close(self):
+        for s in self.slabs:
+            s.close()
+
+    def _all(self, name, *a):
+        return [getattr(s, name)(*a) for s in self.slabs]
+
+    def iterate(self, n, chunk=32):
+        # interleave the slabs' launch queues: a slab's stream waits on its neighbours every step, so
+        # never enqueue one slab far ahead of the others from a single host thread
+        left = int(n)
+        while left > 0:
+            c = min(chunk, left)
+            self._all("advance", c)
+            left -= c
+        self._all("rerender")
+
+    def collide(self):
+        self._all("collide")
+
+    def stream(self):
+        self._all("stream")
+
+    def rerender(self):
+        self._all("rerender")
+
+    def set_summary(self, stat):
+        self._all("set_summary", stat)
+
+    def compute_summary(self, stat):
+        self._all("compute_summary", stat)
+
+    def update_omega_buffer(self, omega):
+        self._all("update_omega_buffer", omega)
+
+    def reset_to_equilibrium(self):
+        self._all("reset_to_equilibrium")
+
+    def custom_speed(self, ux):
+        self._all("custom_speed", ux)
+
+    def single_cell(self, index):
+        self._all("single_cell", index)
+
+    def draw_points(self, pairs):
+        self._all("draw_points", pairs)
+
+    def reset_barrier(self):
+        self._all("reset_barrier")
+
+    def synchronize(self):
+        self._all("synchronize")
+
+    def get_compute_num(self):
+        return self.slabs[0].get_compute_num()
+
+    def read_population(self, k, buffer=-1):
+        return np.concatenate(self._all("read_population", k, buffer), axis=0)
+
+    def read_moments(self):
+        parts = self._all("read_moments")
+        return tuple(np.concatenate([p[q] for p in parts], axis=0) for q in range(3))
+
+    def read_output(self):
+        return np.concatenate(self._all("read_output"), axis=0)
+
+    def read_barrier(self):
+        return np.concatenate(self._all("read_barrier"), axis=0)
+
+    def read_cell_class(self):
+        return np.concatenate(self._all("read_cell_class"), axis=0)
