@@ -97,6 +97,11 @@ int blbm_advance(blbm_t *h, uint32_t n);
  * returns the device time in milliseconds.  (Measurement hook; not in the reference.) */
 int blbm_iterate_timed(blbm_t *h, uint32_t n, float *elapsed_ms);
 
+/* Device stopwatch on the handle's stream: start records an event, stop records another, waits for it
+ * and returns the milliseconds between them — everything enqueued in between, copies included. */
+int blbm_timer_start(blbm_t *h);
+int blbm_timer_stop(blbm_t *h, float *elapsed_ms);
+
 /* pub fn collide / pub fn stream, lbm.rs:1118-1134: one half-step on the live buffer pair; neither
  * touches compute_step (only compute_step() does, lbm.rs:1112-1116). */
 int blbm_collide(blbm_t *h);
@@ -134,6 +139,11 @@ int blbm_draw_points(blbm_t *h, const uint32_t *loc_val_pairs, size_t npairs);
 int blbm_draw_points64(blbm_t *h, const uint64_t *loc_val_pairs, size_t npairs);
 /* LBM::reset_barrier, lbm.rs:1362-1365 */
 int blbm_reset_barrier(blbm_t *h);
+/* Whole-row mask upload — what reset_barrier does with queue.write_buffer(&barrier_buffer, ..)
+ * (lbm.rs:1362-1365), for an arbitrary mask: rows [row_begin, row_begin + nrows) of the GLOBAL lattice,
+ * nrows x W bytes, 1 = barrier.  Rows outside this slab's window (own rows +-2) are ignored, so every
+ * slab may be handed the same data or just its own window. */
+int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const uint8_t *mask);
 
 /* ---- counters, lbm.rs:1166-1172 ---------------------------------------------------------------- */
 uint64_t blbm_get_compute_num(const blbm_t *h);

@@ -655,6 +655,23 @@ int blbm_iterate_timed(blbm_t *h, uint32_t n, float *elapsed_ms)
     return check_peer_err(h);
 }
 
+int blbm_timer_start(blbm_t *h)
+{
+    CKH(h);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    return BLBM_OK;
+}
+
+int blbm_timer_stop(blbm_t *h, float *elapsed_ms)
+{
+    CKH(h);
+    if (!elapsed_ms) return fail(BLBM_EINVAL, "elapsed_ms is null");
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    return check_peer_err(h);
+}
+
 int blbm_collide(blbm_t *h)
 {
     CKH(h);
@@ -796,6 +813,24 @@ int blbm_reset_barrier(blbm_t *h)
     CKH(h);
     CK(launch_mask_init(h->mask, geom(h), h->stream));
     h->launches++;
+    return rebuild_class(h);
+}
+
+int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const uint8_t *mask)
+{
+    CKH(h);
+    if (!mask && nrows) return fail(BLBM_EINVAL, "mask is null");
+    // intersect with the mask window [row0-2, row1+2) and with the lattice
+    const uint64_t win_lo = h->row0 >= 2 ? h->row0 - 2 : 0;
+    const uint64_t win_hi = std::min<uint64_t>(h->Hg, h->row1 + 2);
+    const uint64_t lo = std::max<uint64_t>(row_begin, win_lo);
+    const uint64_t hi = std::min<uint64_t>(row_begin + nrows, win_hi);
+    if (lo < hi) {
+        const int64_t lr = (int64_t)lo - (int64_t)h->row0;
+        CK(cudaMemcpy2DAsync(h->mask + mask_row_off(lr, h->P), h->P, mask + (size_t)(lo - row_begin) * h->W, h->W,
+                             h->W, (size_t)(hi - lo), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));  // the caller's buffer is free again on return
+    }
     return rebuild_class(h);
 }
 

@@ -1,7 +1,7 @@
 // blbm_internal.cuh — device-side data layout, kernel parameter blocks and the BGK collision core
 // shared by every step-kernel implementation.
 //
-// Arithmetic contract ("oracle semantics"): fp32, every binary op individually
+// Arithmetic contract (normative semantics block): fp32, every binary op individually
 // rounded, IEEE division, association exactly as the reference WGSL writes it.  This translation unit
 // is compiled with -fmad=false and the core below additionally spells every op with __f*_rn
 // intrinsics, which the compiler never contracts into FMAs.

@@ -89,6 +89,9 @@ PROTOTYPES = {
     "blbm_draw_points": (_I, [_P, _P, _SZ]),
     "blbm_draw_points64": (_I, [_P, _P, _SZ]),
     "blbm_reset_barrier": (_I, [_P]),
+    "blbm_write_barrier_rows": (_I, [_P, _U64, _U64, _P]),
+    "blbm_timer_start": (_I, [_P]),
+    "blbm_timer_stop": (_I, [_P, C.POINTER(_F)]),
     "blbm_get_compute_num": (_U64, [_P]),
     "blbm_get_frame_num": (_U64, [_P]),
     "blbm_read_population": (_I, [_P, _I, _I, _P]),
@@ -240,6 +243,20 @@ class LBM:
 
     def reset_barrier(self):
         _check(self._L.blbm_reset_barrier(self._h))
+
+    def write_barrier_rows(self, row_begin, mask_rows):
+        """mask_rows: (nrows, W) uint8, 1 = barrier, for global rows [row_begin, row_begin+nrows)."""
+        a = np.ascontiguousarray(mask_rows, dtype=np.uint8)
+        assert a.ndim == 2 and a.shape[1] == self.x
+        _check(self._L.blbm_write_barrier_rows(self._h, int(row_begin), a.shape[0], a.ctypes.data))
+
+    def timer_start(self):
+        _check(self._L.blbm_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = _F()
+        _check(self._L.blbm_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def get_compute_num(self):
         return int(self._L.blbm_get_compute_num(self._h))

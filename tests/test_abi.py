@@ -1,0 +1,85 @@
+"""The C-ABI library loads and exports every symbol include/blbm.h declares; the ctypes prototype table
+of the Python mirror covers exactly the same set; without a GPU every entry point fails loudly (there is
+no CPU fallback).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import lbm_b200
+from lbm_b200 import lbm as host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "blbm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(blbm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_surface():
+    syms = declared_symbols()
+    # one entry point per public method of `pub struct LBM` (lbm.rs:726-1515) that is on the hot path
+    for name in ("blbm_create", "blbm_destroy", "blbm_iterate", "blbm_collide", "blbm_stream", "blbm_rerender",
+                 "blbm_set_summary", "blbm_set_omega", "blbm_reset_to_equilibrium", "blbm_custom_speed",
+                 "blbm_single_cell", "blbm_draw_points", "blbm_reset_barrier", "blbm_get_compute_num",
+                 "blbm_get_frame_num", "blbm_read_population", "blbm_read_moments", "blbm_read_output",
+                 "blbm_read_barrier", "blbm_read_cell_class"):
+        assert name in syms
+
+
+def test_library_exports_every_declared_symbol():
+    path = lbm_b200.library_path()
+    assert os.path.exists(path), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    lib = C.CDLL(path)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"declared in blbm.h but not exported: {missing}"
+
+
+def test_python_prototypes_cover_the_header_exactly():
+    assert sorted(host.PROTOTYPES) == declared_symbols()
+    lib = lbm_b200.load_library()
+    assert lib.blbm_abi_version() == 1
+    assert isinstance(lib.blbm_last_error(), bytes)
+
+
+def test_library_has_no_link_time_dependency_on_the_driver_or_torch():
+    """dlopen must work on a machine without libcuda.so.1 (this container): cudart is linked statically."""
+    import subprocess
+    out = subprocess.run(["ldd", lbm_b200.library_path()], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libcudart" not in out and "torch" not in out
+
+
+def test_without_a_gpu_the_product_fails_loudly():
+    lib = lbm_b200.load_library()
+    n = lib.blbm_device_count()
+    if n > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(lbm_b200.BlbmError) as e:
+        lbm_b200.LBM(1.25, 64, 32)
+    assert e.value.code == -4  # BLBM_ENOGPU
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under lbm_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("lbm_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                    if "oracle" in open(os.path.join(dirpath, f), errors="ignore").read().lower():
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+
+
+def test_slab_rows_partition():
+    from lbm_b200.lbm import slab_rows
+    for y, n in ((50, 3), (16384 * 8, 8), (7, 2), (65536, 8)):
+        r = slab_rows(y, n)
+        assert r[0][0] == 0 and r[-1][1] == y
+        assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        sizes = [b - a for a, b in r]
+        assert max(sizes) - min(sizes) <= 1

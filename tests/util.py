@@ -14,7 +14,9 @@ def assert_same_bits(a, b, what):
     b = np.ascontiguousarray(b)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
     if a.dtype == np.float32:
-        bad = bits(a) != bits(b)
+        # bit-exact, except that NaN payload/sign bits are not compared: IEEE 754 (and WGSL) leave them
+        # implementation-defined, and x86 SSE and the GPU pick different quiet-NaN patterns
+        bad = (bits(a) != bits(b)) & ~(np.isnan(a) & np.isnan(b))
     else:
         bad = a != b
     if bad.any():
@@ -85,7 +87,7 @@ def random_script(rng, w, h, phases=6, max_steps=40, max_pts=30):
         val = rng.integers(0, 2, size=loc.size)
         script.append(("draw", np.stack([loc, val], 1).astype(np.uint32)))
         if ph == 1:
-            script.append(("omega", 1.9))
+            script.append(("omega", 1.6))
         if ph == 2:
             script += [("summary", s) for s in (1, 2, 3, 4, 0)]
             script.append(("compare",))
