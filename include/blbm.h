@@ -198,6 +198,13 @@ int blbm_exchange_halos(blbm_t *h);
 /* ---- tuning / measurement -------------------------------------------------------------------- */
 int blbm_set_kernel(blbm_t *h, int kernel); /* blbm_kernel */
 int blbm_get_kernel(const blbm_t *h);       /* the resolved implementation (never AUTO) */
+/* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale
+ * copies; the collision shaders have no mask test), so their state can live in a compact side table that is advanced in
+ * registers, which removes their memory traffic from the step kernel.  Results are bit-identical either
+ * way.  mode: 0 never, 1 always, 2 auto (default: when >= 2 % of the cells are barriers and a call runs
+ * >= 8 steps). */
+int blbm_set_lazy_barriers(blbm_t *h, int mode);
+int blbm_get_lazy_barriers_active(const blbm_t *h);
 /* kernels launched by this handle since creation (the bench's gpu_launches claim) */
 uint64_t blbm_get_launch_count(const blbm_t *h);
 /* device bytes held by the handle */

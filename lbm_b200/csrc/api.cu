@@ -79,6 +79,10 @@ struct blbm {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // asynchronous read-back of the output field: a second stream so the copy overlaps later steps
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_sum = nullptr, ev_copy = nullptr;
+    bool copy_pending = false;
     uint32_t W = 0, P = 0, rows = 0;
     uint64_t Hg = 0, row0 = 0, row1 = 0;
     size_t plane = 0;  // elements per population plane, (rows+3)*P
@@ -108,6 +112,14 @@ struct blbm {
     unsigned long long wait_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
     uint64_t *d_pairs = nullptr;
     size_t d_pairs_cap = 0;
+    // barrier chains (lazy barrier cells): see aux_kernels.cu
+    int lazy_mode = 2;           // 0 never, 1 always, 2 auto (enough barrier cells and enough steps to pay off)
+    bool chain_active = false;   // barrier slots of the planes are don't-care, their state is in the table
+    bool chain_declined = false; // auto mode looked at the current mask and decided against
+    uint32_t *chain_idx = nullptr;
+    float *chain_state = nullptr;
+    size_t chain_n = 0, chain_cap = 0;
+    unsigned long long *chain_counter = nullptr;
 };
 
 namespace {
@@ -188,6 +200,76 @@ int signal_peers(blbm *h)
 
 int push_all_halos(blbm *h);
 
+ChainPlanes chain_planes(const blbm *h)
+{
+    ChainPlanes pl;
+    for (int d = 0; d < 8; d++) {
+        pl.f0[d] = h->f[0][d];
+        pl.f1[d] = h->f[1][d];
+    }
+    pl.R = h->R;
+    return pl;
+}
+
+// table -> planes: afterwards every barrier slot again holds exactly what the reference's buffers hold
+int chain_flush(blbm *h)
+{
+    if (!h->chain_active) return BLBM_OK;
+    CK(launch_chain_flush(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, chain_planes(h), h->cls[0],
+                          h->cls[1], h->stream));
+    h->launches++;
+    h->chain_active = false;
+    return BLBM_OK;
+}
+
+// Stream-ordered allocation: cudaMalloc/cudaFree synchronise the whole device, which deadlocks when a
+// sibling slab of the same process has a wait kernel queued on this slab's next signal.
+cudaError_t stream_alloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes, st); }
+void stream_free(void *p, cudaStream_t st)
+{
+    if (p) cudaFreeAsync(p, st);
+}
+
+// planes -> table, if it pays off.  Never fails the caller: on any shortage the dense path stays in use.
+int chain_try_enter(blbm *h, uint32_t steps_left)
+{
+    if (h->chain_active || h->lazy_mode == 0 || h->chain_declined || h->cls_pending) return BLBM_OK;
+    if (h->lazy_mode == 2 && steps_left < 8) return BLBM_OK;
+    if (h->plane >= 0xffffffffull) return BLBM_OK;
+    CK(launch_chain_count(h->cls[h->cls_cur], geom(h), h->chain_counter, h->stream));
+    h->launches++;
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, h->chain_counter, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const unsigned long long cells = (unsigned long long)h->rows * h->W;
+    if (n == 0 || (h->lazy_mode == 2 && n * 50ull < cells)) {
+        h->chain_declined = true;
+        return BLBM_OK;
+    }
+    if (h->chain_cap < n) {
+        stream_free(h->chain_idx, h->stream);
+        stream_free(h->chain_state, h->stream);
+        h->chain_idx = nullptr;
+        h->chain_state = nullptr;
+        h->chain_cap = 0;
+        if (stream_alloc((void **)&h->chain_idx, n * sizeof(uint32_t), h->stream) != cudaSuccess ||
+            stream_alloc((void **)&h->chain_state, n * 17 * sizeof(float), h->stream) != cudaSuccess) {
+            cudaGetLastError();
+            stream_free(h->chain_idx, h->stream);
+            h->chain_idx = nullptr;
+            h->chain_declined = true;  // not enough memory: stay dense
+            return BLBM_OK;
+        }
+        h->chain_cap = (size_t)n;
+    }
+    CK(launch_chain_build(h->cls[h->cls_cur], geom(h), chain_planes(h), h->chain_idx, h->chain_state, h->chain_cap,
+                          h->chain_counter, h->stream));
+    h->launches++;
+    h->chain_n = (size_t)n;
+    h->chain_active = true;
+    return BLBM_OK;
+}
+
 int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
 {
     StepParams p;
@@ -250,6 +332,7 @@ int run_summary(blbm *h)
 {
     int rc = sync_peers(h);  // curl reads the moment halo rows
     if (rc) return rc;
+    if (h->copy_pending) CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));  // the copy still reads `out`
     CK(launch_summary(h->stat, h->mx, h->my, h->rho, h->out, geom(h), h->stream));
     h->launches++;
     return BLBM_OK;
@@ -258,9 +341,19 @@ int run_summary(blbm *h)
 int do_steps(blbm *h, uint32_t n)
 {
     uint32_t left = n;
+    bool replayed = false;
     while (left) {
         const bool mom = left == 1;
         int rc;
+        if (!h->chain_active && (rc = chain_try_enter(h, left)) != BLBM_OK) return rc;
+        if (h->chain_active && !replayed) {
+            // barrier cells do not depend on anything else: advance their chains through all the steps of
+            // this call up front, in registers; this also stores the moments of the call's last collide
+            CK(launch_chain_replay(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, left,
+                                   (uint32_t)(h->step % 2), h->omega, h->mx, h->my, h->rho, h->stream));
+            h->launches++;
+            replayed = true;
+        }
         if (!h->regimeT) {
             // collide of step `step`, in place on the live buffer (collision/*.wgsl); its stream stays pending
             const int y = (int)(h->step % 2);
@@ -282,9 +375,11 @@ int do_steps(blbm *h, uint32_t n)
 
 int rebuild_class(blbm *h)
 {
+    h->chain_declined = false;  // new mask: auto mode decides afresh (callers flushed the table already)
     // in the T-regime the pending stream must still see the old classification
     const int target = h->regimeT ? (h->cls_cur ^ 1) : h->cls_cur;
-    CK(launch_build_class(h->cls[target], h->mask, geom(h), h->stream));
+    CK(launch_build_class(h->cls[target], h->mask, geom(h), h->chain_active ? h->cls[h->cls_cur] : nullptr,
+                          h->stream));
     h->launches++;
     if (h->regimeT) h->cls_pending = true;
     return BLBM_OK;
@@ -376,6 +471,7 @@ int fill_equilibrium(blbm *h, float ux, int single_index)
     h->step = 0;
     h->frame = 0;
     h->regimeT = false;
+    h->chain_active = false;  // the table described the old populations
     consume_pending_class(h);
     h->halo_dirty = false;  // every slab filled its halo rows with the same constants
     return BLBM_OK;
@@ -407,6 +503,10 @@ int check_peer_err(blbm *h)
 int sync_stream(blbm *h)
 {
     CK(cudaStreamSynchronize(h->stream));
+    if (h->copy_pending) {
+        CK(cudaStreamSynchronize(h->copy_stream));
+        h->copy_pending = false;
+    }
     return check_peer_err(h);
 }
 
@@ -550,7 +650,7 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     const size_t off_cls0 = carve(h->plane * sizeof(uint16_t)), off_cls1 = carve(h->plane * sizeof(uint16_t));
     const size_t off_mask = carve((size_t)(h->rows + 4) * h->P);
     h->off_flags = carve(256);
-    const size_t off_err = carve(64), off_red = carve(64);
+    const size_t off_err = carve(64), off_red = carve(64), off_cnt = carve(64);
     h->pool_bytes = off;
     e = cudaMalloc(&h->pool, h->pool_bytes);
     if (e != cudaSuccess) {
@@ -571,19 +671,23 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     h->err_flag = reinterpret_cast<int *>(h->pool + off_err);
     h->red_sums = reinterpret_cast<double *>(h->pool + off_red);
     h->red_max = reinterpret_cast<float *>(h->pool + off_red + 32);
+    h->chain_counter = reinterpret_cast<unsigned long long *>(h->pool + off_cnt);
 
     int rc = BLBM_OK;
     do {
         cudaError_t ce;
         if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+            (ce = cudaEventCreateWithFlags(&h->ev_sum, cudaEventDisableTiming)) != cudaSuccess ||
+            (ce = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
             (ce = cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->stream)) != cudaSuccess) {
             rc = fail(BLBM_ECUDA, "handle setup failed: %s", cudaGetErrorString(ce));
             break;
         }
         if ((rc = fill_equilibrium(h, inflow_ux, -1)) != BLBM_OK) break;
         if ((ce = launch_mask_init(h->mask, geom(h), h->stream)) != cudaSuccess ||
-            (ce = launch_build_class(h->cls[0], h->mask, geom(h), h->stream)) != cudaSuccess) {
+            (ce = launch_build_class(h->cls[0], h->mask, geom(h), nullptr, h->stream)) != cudaSuccess) {
             rc = fail(BLBM_ECUDA, "mask setup failed: %s", cudaGetErrorString(ce));
             break;
         }
@@ -613,10 +717,21 @@ int blbm_destroy(blbm_t *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->up.ipc_opened) cudaIpcCloseMemHandle(h->up.base);
     if (h->dn.ipc_opened) cudaIpcCloseMemHandle(h->dn.base);
-    if (h->d_pairs) cudaFree(h->d_pairs);
+    if (h->stream) {
+        stream_free(h->d_pairs, h->stream);
+        stream_free(h->chain_idx, h->stream);
+        stream_free(h->chain_state, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
     if (h->pool) cudaFree(h->pool);
+    if (h->copy_stream) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamDestroy(h->copy_stream);
+    }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_sum) cudaEventDestroy(h->ev_sum);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return BLBM_OK;
@@ -666,6 +781,7 @@ int blbm_timer_stop(blbm_t *h, float *elapsed_ms)
 {
     CKH(h);
     if (!elapsed_ms) return fail(BLBM_EINVAL, "elapsed_ms is null");
+    if (h->copy_pending) CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));  // the stopwatch covers the copy
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
@@ -675,7 +791,9 @@ int blbm_timer_stop(blbm_t *h, float *elapsed_ms)
 int blbm_collide(blbm_t *h)
 {
     CKH(h);
-    int rc = materialise(h);
+    int rc = chain_flush(h);
+    if (rc) return rc;
+    rc = materialise(h);
     if (rc) return rc;
     const int y = (int)(h->step % 2);
     return launch_step(h, MODE_COLLIDE_ONLY, y, y, true);
@@ -684,7 +802,9 @@ int blbm_collide(blbm_t *h)
 int blbm_stream(blbm_t *h)
 {
     CKH(h);
-    int rc = materialise(h);
+    int rc = chain_flush(h);
+    if (rc) return rc;
+    rc = materialise(h);
     if (rc) return rc;
     const int x = (int)(h->step % 2), y = (int)((h->step + 1) % 2);
     return launch_step(h, MODE_STREAM_ONLY, x, y, false);
@@ -773,18 +893,21 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
     const size_t nu = uniq.size() / 2;
     if (nu) {
         if (h->d_pairs_cap < nu) {
-            if (h->d_pairs) {
-                CK(cudaStreamSynchronize(h->stream));
-                CK(cudaFree(h->d_pairs));
-                h->d_pairs = nullptr;
-                h->d_pairs_cap = 0;
-            }
+            stream_free(h->d_pairs, h->stream);
+            h->d_pairs = nullptr;
+            h->d_pairs_cap = 0;
             const size_t cap = std::max<size_t>(nu, 4096);
-            cudaError_t e = cudaMalloc(&h->d_pairs, cap * 2 * sizeof(uint64_t));
-            if (e != cudaSuccess) return fail(BLBM_ENOMEM, "cudaMalloc for paint list failed");
+            cudaError_t e = stream_alloc((void **)&h->d_pairs, cap * 2 * sizeof(uint64_t), h->stream);
+            if (e != cudaSuccess) return fail(BLBM_ENOMEM, "allocating the paint list failed");
             h->d_pairs_cap = cap;
         }
         CK(cudaMemcpyAsync(h->d_pairs, uniq.data(), nu * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        if (h->chain_active) {
+            // cells about to change leave the chain table first (their state returns to the planes)
+            CK(launch_chain_evict(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, chain_planes(h),
+                                  h->cls[h->cls_cur], h->cls[h->cls_cur ^ 1], geom(h), h->d_pairs, nu, h->stream));
+            h->launches += 3;
+        }
         CK(launch_mask_scatter(h->mask, geom(h), h->d_pairs, nu, h->stream));
         h->launches++;
         CK(cudaStreamSynchronize(h->stream));  // uniq is pageable host memory owned by this frame
@@ -811,6 +934,10 @@ int blbm_draw_points(blbm_t *h, const uint32_t *pairs, size_t npairs)
 int blbm_reset_barrier(blbm_t *h)
 {
     CKH(h);
+    {
+        int rcf = chain_flush(h);
+        if (rcf) return rcf;
+    }
     CK(launch_mask_init(h->mask, geom(h), h->stream));
     h->launches++;
     return rebuild_class(h);
@@ -820,6 +947,10 @@ int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const
 {
     CKH(h);
     if (!mask && nrows) return fail(BLBM_EINVAL, "mask is null");
+    {
+        int rcf = chain_flush(h);
+        if (rcf) return rcf;
+    }
     // intersect with the mask window [row0-2, row1+2) and with the lattice
     const uint64_t win_lo = h->row0 >= 2 ? h->row0 - 2 : 0;
     const uint64_t win_hi = std::min<uint64_t>(h->Hg, h->row1 + 2);
@@ -856,7 +987,9 @@ int blbm_read_population(blbm_t *h, int buffer, int k, float *dst)
 {
     CKH(h);
     if (!dst || k < 0 || k > 8 || buffer < -1 || buffer > 1) return fail(BLBM_EINVAL, "bad argument");
-    int rc = materialise(h);
+    int rc = chain_flush(h);
+    if (rc) return rc;
+    rc = materialise(h);
     if (rc) return rc;
     rc = copy_plane_to_host(h, population_plane(h, buffer, k), dst);
     if (rc) return rc;
@@ -867,7 +1000,9 @@ int blbm_write_population(blbm_t *h, int buffer, int k, const float *src)
 {
     CKH(h);
     if (!src || k < 0 || k > 8 || buffer < -1 || buffer > 1) return fail(BLBM_EINVAL, "bad argument");
-    int rc = materialise(h);
+    int rc = chain_flush(h);
+    if (rc) return rc;
+    rc = materialise(h);
     if (rc) return rc;
     float *plane = population_plane(h, buffer, k);
     CK(cudaMemcpy2DAsync(plane + row_off(0, h->P), (size_t)h->P * sizeof(float), src, (size_t)h->W * sizeof(float),
@@ -899,7 +1034,17 @@ int blbm_read_output_async(blbm_t *h, float *pinned_dst)
 {
     CKH(h);
     if (!pinned_dst) return fail(BLBM_EINVAL, "dst is null");
-    return copy_plane_to_host(h, h->out, pinned_dst);
+    // order the copy after everything enqueued so far, but run it on the copy stream so that the steps
+    // enqueued next overlap it; the next summary launch waits for it (it overwrites `out`)
+    if (h->copy_pending) CK(cudaStreamWaitEvent(h->copy_stream, h->ev_copy, 0));
+    CK(cudaEventRecord(h->ev_sum, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_sum, 0));
+    CK(cudaMemcpy2DAsync(pinned_dst, (size_t)h->W * sizeof(float), h->out + row_off(0, h->P),
+                         (size_t)h->P * sizeof(float), (size_t)h->W * sizeof(float), h->rows, cudaMemcpyDeviceToHost,
+                         h->copy_stream));
+    CK(cudaEventRecord(h->ev_copy, h->copy_stream));
+    h->copy_pending = true;
+    return BLBM_OK;
 }
 
 int blbm_synchronize(blbm_t *h)
@@ -933,7 +1078,11 @@ int blbm_read_cell_class(blbm_t *h, uint16_t *dst)
     const uint16_t *c = h->cls[h->cls_pending ? (h->cls_cur ^ 1) : h->cls_cur];  // class of the current mask
     CK(cudaMemcpy2DAsync(dst, (size_t)h->W * 2, c + row_off(0, h->P), (size_t)h->P * 2, (size_t)h->W * 2, h->rows,
                          cudaMemcpyDeviceToHost, h->stream));
-    return sync_stream(h);
+    int rc = sync_stream(h);
+    if (rc) return rc;
+    const size_t ncell = (size_t)h->rows * h->W;
+    for (size_t q = 0; q < ncell; q++) dst[q] &= CLS_PUBLIC;  // drop the internal chain-table bits
+    return BLBM_OK;
 }
 
 int blbm_reduce_moments(blbm_t *h, double *sum_rho, double *sum_mx, double *sum_my, float *max_abs_output)
@@ -1029,7 +1178,9 @@ int blbm_exchange_halos(blbm_t *h)
 {
     CKH(h);
     if (!any_peer(h)) return BLBM_OK;
-    int rc = materialise(h);
+    int rc = chain_flush(h);
+    if (rc) return rc;
+    rc = materialise(h);
     if (rc) return rc;
     return push_all_halos(h);
 }
@@ -1047,6 +1198,21 @@ int blbm_set_kernel(blbm_t *h, int kernel)
 }
 
 int blbm_get_kernel(const blbm_t *h) { return h ? h->kernel : BLBM_EINVAL; }
+
+int blbm_set_lazy_barriers(blbm_t *h, int mode)
+{
+    CKH(h);
+    if (mode < 0 || mode > 2) return fail(BLBM_EINVAL, "mode %d out of range", mode);
+    if (mode == 0) {
+        int rc = chain_flush(h);
+        if (rc) return rc;
+    }
+    h->lazy_mode = mode;
+    h->chain_declined = false;
+    return BLBM_OK;
+}
+
+int blbm_get_lazy_barriers_active(const blbm_t *h) { return h && h->chain_active ? 1 : 0; }
 uint64_t blbm_get_launch_count(const blbm_t *h) { return h ? h->launches : 0; }
 uint64_t blbm_get_device_bytes(const blbm_t *h) { return h ? h->pool_bytes : 0; }
 

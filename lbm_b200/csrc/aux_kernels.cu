@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t mask_at(const uint8_t *mask, const SlabGeom 
     return mask[mask_row_off(lr, g.P) + (size_t)gx];
 }
 
-__global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const SlabGeom g)
+__global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const SlabGeom g, const uint16_t *keep_chain)
 {
     const size_t total = (size_t)g.rows * g.P;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -131,14 +131,18 @@ __global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const Sla
 #pragma unroll
             for (int d = 0; d < 8; d++)
                 if (mask_at(mask, g, (int64_t)x - dir_dx(d), gy - dir_dy(d)) == 1) c |= cls_upstream_bit(d);
+            // cells whose state lives in the chain table stay there (a paint evicts the cells it touches
+            // before the mask changes, so a kept bit always belongs to a cell that is still a barrier)
+            if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & CLS_CHAIN;
         }
         cls[row_off(r, g.P) + x] = c;
     }
 }
 
-cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, cudaStream_t st)
+cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, const uint16_t *keep_chain,
+                               cudaStream_t st)
 {
-    build_class_kernel<<<148 * 8, 256, 0, st>>>(cls, mask, g);
+    build_class_kernel<<<148 * 8, 256, 0, st>>>(cls, mask, g, keep_chain);
     return cudaGetLastError();
 }
 
@@ -352,6 +356,239 @@ cudaError_t launch_wait(const unsigned long long *from_up, const unsigned long l
                         cudaStream_t st)
 {
     wait_kernel<<<1, 1, 0, st>>>(from_up, from_dn, epoch, err_flag, timeout_ns);
+    return cudaGetLastError();
+}
+
+}  // namespace blbmk
+
+// ================================================================================================
+// Barrier chains.  A barrier cell is never read by any other cell (its neighbours bounce back instead
+// of pulling from it) and is never written by a stream pass, so all the reference does to it is
+// collide the stale copy in buffer step%2 — in place, every step, sharing one rest population
+// (collision/*.wgsl have no mask test).  That is a closed 17-float recurrence per cell.  The chain
+// table holds those 17 floats compactly; chain_replay_kernel advances them n steps in registers with
+// the very same collide_cell() the step kernels use (bit-identical by construction) and stores the
+// moments of the last collide where the summary kernels expect them.
+// Layout: state[c*cap + e], c = 0..7 buffer-0 populations (Dir order), 8..15 buffer-1, 16 rest.
+// ================================================================================================
+namespace blbmk {
+
+__global__ void chain_count_kernel(const uint16_t *cls, const SlabGeom g, unsigned long long *count)
+{
+    unsigned long long local = 0;
+    const size_t total = (size_t)g.rows * g.P;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x)
+        local += (cls[(size_t)g.P + t] & CLS_BARRIER) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, unsigned long long *count,
+                               cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    chain_count_kernel<<<148 * 8, 256, 0, st>>>(cls, g, count);
+    return cudaGetLastError();
+}
+
+__global__ void chain_build_kernel(uint16_t *cls, const SlabGeom g, const ChainPlanes pl, uint32_t *idx,
+                                   float *state, size_t cap, unsigned long long *cursor)
+{
+    const size_t total = (size_t)g.rows * g.P;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = (size_t)g.P + t;  // plane offset of an owned cell (incl. pitch padding: class 0)
+        const uint16_t c = cls[i];
+        if (!(c & CLS_BARRIER)) continue;
+        const size_t e = (size_t)atomicAdd(cursor, 1ull);
+        if (e >= cap) continue;
+        cls[i] = c | CLS_CHAIN;
+        idx[e] = (uint32_t)i;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            state[(size_t)d * cap + e] = pl.f0[d][i];
+            state[(size_t)(8 + d) * cap + e] = pl.f1[d][i];
+        }
+        state[(size_t)16 * cap + e] = pl.R[i];
+    }
+}
+
+cudaError_t launch_chain_build(uint16_t *cls, const SlabGeom &g, const ChainPlanes &pl, uint32_t *idx,
+                               float *state, size_t cap, unsigned long long *cursor, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    chain_build_kernel<<<148 * 8, 256, 0, st>>>(cls, g, pl, idx, state, cap, cursor);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ void chain_store_entry(const float *state, size_t cap, size_t e, const ChainPlanes &pl,
+                                                  size_t i)
+{
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        pl.f0[d][i] = state[(size_t)d * cap + e];
+        pl.f1[d][i] = state[(size_t)(8 + d) * cap + e];
+    }
+    pl.R[i] = state[(size_t)16 * cap + e];
+}
+
+__global__ void chain_flush_kernel(const uint32_t *idx, const float *state, size_t n, size_t cap,
+                                   const ChainPlanes pl, uint16_t *cls0, uint16_t *cls1)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t ie = idx[e];
+        if (ie == CHAIN_DEAD) continue;
+        const size_t i = ie;
+        chain_store_entry(state, cap, e, pl, i);
+        cls0[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
+        cls1[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
+    }
+}
+
+cudaError_t launch_chain_flush(const uint32_t *idx, const float *state, size_t n, size_t cap,
+                               const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    size_t nb = (n + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    chain_flush_kernel<<<(unsigned)nb, 256, 0, st>>>(idx, state, n, cap, pl, cls0, cls1);
+    return cudaGetLastError();
+}
+
+// ---- a paint touches some chain cells: move exactly those back into the planes ------------------------
+__device__ __forceinline__ bool pair_to_cell(const SlabGeom &g, uint64_t loc, size_t *i)
+{
+    const uint64_t gy = loc / g.W;
+    if (gy < g.row0 || gy >= g.row0 + g.rows) return false;
+    *i = row_off((uint32_t)(gy - g.row0), g.P) + (size_t)(loc - gy * g.W);
+    return true;
+}
+
+__global__ void chain_mark_kernel(uint16_t *cls, const SlabGeom g, const uint64_t *pairs, size_t npairs)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npairs;
+         t += (size_t)gridDim.x * blockDim.x) {
+        size_t i;
+        if (!pair_to_cell(g, pairs[2 * t], &i)) continue;
+        const uint16_t c = cls[i];
+        if (c & CLS_CHAIN) cls[i] = c | CLS_DIRTY;
+    }
+}
+
+__global__ void chain_evict_kernel(uint32_t *idx, const float *state, size_t n, size_t cap, const ChainPlanes pl,
+                                   const uint16_t *cls)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t ie = idx[e];
+        if (ie == CHAIN_DEAD || !(cls[ie] & CLS_DIRTY)) continue;
+        chain_store_entry(state, cap, e, pl, ie);
+        idx[e] = CHAIN_DEAD;
+    }
+}
+
+__global__ void chain_unmark_kernel(uint16_t *cls_cur, uint16_t *cls_other, const SlabGeom g, const uint64_t *pairs,
+                                    size_t npairs)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npairs;
+         t += (size_t)gridDim.x * blockDim.x) {
+        size_t i;
+        if (!pair_to_cell(g, pairs[2 * t], &i)) continue;
+        cls_cur[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
+        cls_other[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
+    }
+}
+
+cudaError_t launch_chain_evict(uint32_t *idx, const float *state, size_t n, size_t cap, const ChainPlanes &pl,
+                               uint16_t *cls_cur, uint16_t *cls_other, const SlabGeom &g, const uint64_t *pairs,
+                               size_t npairs, cudaStream_t st)
+{
+    if (n == 0 || npairs == 0) return cudaSuccess;
+    size_t nbp = (npairs + 255) / 256;
+    if (nbp > 148 * 16) nbp = 148 * 16;
+    size_t nbe = (n + 255) / 256;
+    if (nbe > 148 * 16) nbe = 148 * 16;
+    chain_mark_kernel<<<(unsigned)nbp, 256, 0, st>>>(cls_cur, g, pairs, npairs);
+    chain_evict_kernel<<<(unsigned)nbe, 256, 0, st>>>(idx, state, n, cap, pl, cls_cur);
+    chain_unmark_kernel<<<(unsigned)nbp, 256, 0, st>>>(cls_cur, cls_other, g, pairs, npairs);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ bool same_bits17(const float (&a)[8], const float (&b)[8], float r, const float (&a0)[8],
+                                            const float (&b0)[8], float r0)
+{
+    bool same = __float_as_uint(r) == __float_as_uint(r0);
+#pragma unroll
+    for (int d = 0; d < 8; d++)
+        same = same && __float_as_uint(a[d]) == __float_as_uint(a0[d]) &&
+               __float_as_uint(b[d]) == __float_as_uint(b0[d]);
+    return same;
+}
+
+// Advance every chain by nsteps collides: step s collides the copy in buffer (parity0 + s) % 2.
+// Exact shortcut: once a pair of steps leaves all 17 floats bit-identical, every later pair does too
+// (same deterministic map, same omega), so the remaining pairs are skipped.
+__global__ void __launch_bounds__(128) chain_replay_kernel(const uint32_t *idx, float *state, size_t n, size_t cap,
+                                                           uint32_t nsteps, uint32_t parity0, float omega,
+                                                           float *mx, float *my, float *rho)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || nsteps == 0) return;
+    if (idx[e] == CHAIN_DEAD) return;  // evicted by a paint
+    float a[8], b[8], R;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        a[d] = state[(size_t)d * cap + e];
+        b[d] = state[(size_t)(8 + d) * cap + e];
+    }
+    R = state[(size_t)16 * cap + e];
+    float m_x = 0.f, m_y = 0.f, r = 0.f;
+    uint32_t left = nsteps;
+    uint32_t par = parity0 & 1u;
+    while (left >= 2) {
+        float a0[8], b0[8];
+        const float R0 = R;
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            a0[d] = a[d];
+            b0[d] = b[d];
+        }
+        if (par == 0) {
+            collide_cell(a, R, omega, m_x, m_y, r);
+            collide_cell(b, R, omega, m_x, m_y, r);
+        } else {
+            collide_cell(b, R, omega, m_x, m_y, r);
+            collide_cell(a, R, omega, m_x, m_y, r);
+        }
+        left -= 2;
+        if (same_bits17(a, b, R, a0, b0, R0)) left &= 1u;  // fixed point of the two-step map
+    }
+    if (left) {
+        if (par == 0) collide_cell(a, R, omega, m_x, m_y, r);
+        else collide_cell(b, R, omega, m_x, m_y, r);
+    }
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        state[(size_t)d * cap + e] = a[d];
+        state[(size_t)(8 + d) * cap + e] = b[d];
+    }
+    state[(size_t)16 * cap + e] = R;
+    const size_t i = idx[e];
+    mx[i] = m_x;
+    my[i] = m_y;
+    rho[i] = r;
+}
+
+cudaError_t launch_chain_replay(const uint32_t *idx, float *state, size_t n, size_t cap, uint32_t nsteps,
+                                uint32_t parity0, float omega, float *mx, float *my, float *rho, cudaStream_t st)
+{
+    if (n == 0 || nsteps == 0) return cudaSuccess;
+    const size_t nb = (n + 127) / 128;
+    if (nb > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    chain_replay_kernel<<<(unsigned)nb, 128, 0, st>>>(idx, state, n, cap, nsteps, parity0, omega, mx, my, rho);
     return cudaGetLastError();
 }
 

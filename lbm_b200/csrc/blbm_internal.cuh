@@ -22,6 +22,12 @@ __host__ __device__ constexpr int dir_opp(int d) { return 7 - d; }
 // class word per cell (also what blbm_read_cell_class returns)
 constexpr uint16_t CLS_BARRIER = 1u;
 constexpr uint16_t CLS_SKIP = 2u;
+// internal bits, masked out of blbm_read_cell_class: the cell's state lives in the barrier-chain table
+// (its plane slots are don't-care), and a scratch mark used while a paint evicts cells from that table
+constexpr uint16_t CLS_CHAIN = 1u << 10;
+constexpr uint16_t CLS_DIRTY = 1u << 11;
+constexpr uint16_t CLS_PUBLIC = 0x3ffu;
+constexpr uint32_t CHAIN_DEAD = 0xffffffffu;
 __host__ __device__ constexpr uint16_t cls_upstream_bit(int d) { return (uint16_t)(4u << d); }
 
 // Where the cells that a neighbouring slab gathers from get mirrored (direct stores into the peer
@@ -146,7 +152,9 @@ cudaError_t launch_fill_rows(float *const *planes, const float *values, int npla
 cudaError_t launch_mask_init(uint8_t *mask, const SlabGeom &g, cudaStream_t st);
 cudaError_t launch_mask_scatter(uint8_t *mask, const SlabGeom &g, const uint64_t *pairs, size_t npairs,
                                 cudaStream_t st);
-cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, cudaStream_t st);
+// keep_chain (may alias cls, may be null): class words whose CLS_CHAIN bit is carried over
+cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, const uint16_t *keep_chain,
+                               cudaStream_t st);
 cudaError_t launch_precollision_moments(const float *const *f8, float *mx, float *my, float *rho, uint32_t W,
                                         uint32_t P, uint32_t dev_row_begin, uint32_t dev_row_end,
                                         cudaStream_t st);
@@ -154,6 +162,24 @@ cudaError_t launch_summary(int stat, const float *mx, const float *my, const flo
                            const SlabGeom &g, cudaStream_t st);
 cudaError_t launch_reduce(const float *mx, const float *my, const float *rho, const float *out,
                           const SlabGeom &g, double *sums3, float *maxabs, cudaStream_t st);
+// barrier chains (see aux_kernels.cu)
+struct ChainPlanes {
+    float *f0[8], *f1[8], *R;
+};
+cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, unsigned long long *count,
+                               cudaStream_t st);
+cudaError_t launch_chain_build(uint16_t *cls, const SlabGeom &g, const ChainPlanes &pl, uint32_t *idx,
+                               float *state, size_t cap, unsigned long long *cursor, cudaStream_t st);
+cudaError_t launch_chain_flush(const uint32_t *idx, const float *state, size_t n, size_t cap,
+                               const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1, cudaStream_t st);
+// a paint is about to change the mask at `pairs` (global location, value): move those cells' chains back
+// into the planes and drop them from the table
+cudaError_t launch_chain_evict(uint32_t *idx, const float *state, size_t n, size_t cap, const ChainPlanes &pl,
+                               uint16_t *cls_cur, uint16_t *cls_other, const SlabGeom &g, const uint64_t *pairs,
+                               size_t npairs, cudaStream_t st);
+cudaError_t launch_chain_replay(const uint32_t *idx, float *state, size_t n, size_t cap, uint32_t nsteps,
+                                uint32_t parity0, float omega, float *mx, float *my, float *rho, cudaStream_t st);
+
 cudaError_t launch_signal(unsigned long long *remote_up, unsigned long long *remote_dn,
                           unsigned long long epoch, cudaStream_t st);
 cudaError_t launch_wait(const unsigned long long *from_up, const unsigned long long *from_dn,

@@ -10,6 +10,13 @@
 // half-way bounce-back, e_w_stream.wgsl:51-62 etc.), a skipped cell (barrier | x==0 | y>=H-1,
 // e_w_stream.wgsl:31-45) re-reads its own stale copy from Y, then every cell is collided and written
 // to Y.  9 fp32 loads + 9 fp32 stores per cell = 72 B, the algorithmic minimum of a two-lattice D2Q9.
+//
+// Chain cells (class bit CLS_CHAIN): barrier cells are isolated — no other cell ever reads their
+// populations — so their two collide-only chains can be kept in a compact side table and replayed in
+// registers (aux_kernels.cu, barrier-chain kernels).  The step kernels treat the plane slots of such
+// cells as don't-care: they neither re-read them from Y (the sector-granular re-read costs ~30 B/cell
+// on a 15 % porous mask) nor store anything meaningful there, and a moment-storing launch keeps the
+// moments the chain kernel already put there.
 #include "blbm_internal.cuh"
 
 namespace blbmk {
@@ -33,6 +40,12 @@ __device__ __forceinline__ size_t pull_src(const size_t i, const uint32_t x, con
     return (size_t)((ptrdiff_t)i - dx - (ptrdiff_t)dy * (ptrdiff_t)P);
 }
 
+// does a cell with class word c continue from its own copy in the destination buffer?
+__device__ __forceinline__ bool reloads_own(const uint32_t c)
+{
+    return (c & (CLS_SKIP | CLS_CHAIN)) == CLS_SKIP;
+}
+
 // ------------------------------------------------------------------------------------------------
 // scalar kernel: one cell per thread.  Used for the collide-only and stream-only passes, for tiny
 // lattices and as the in-GPU cross-check of the vectorised kernels.
@@ -48,12 +61,18 @@ __global__ void __launch_bounds__(128) step_scalar_kernel(const StepParams p)
     const size_t i = row_off(r, p.P) + x;
     const uint16_t c = p.cls[i];
     const bool skipped = (c & CLS_SKIP) != 0;
+    const bool lazy_barrier = (c & CLS_CHAIN) != 0;
 
     float f[8];
     if (MODE == MODE_STREAM_ONLY && skipped) return;  // destination untouched, like the WGSL early return
     if (MODE == MODE_COLLIDE_ONLY || (MODE == MODE_FUSED && skipped)) {
+        if (lazy_barrier && MODE == MODE_FUSED) {
 #pragma unroll
-        for (int d = 0; d < 8; d++) f[d] = p.Y[d][i];
+            for (int d = 0; d < 8; d++) f[d] = 0.0625f;  // don't-care slot: no load
+        } else {
+#pragma unroll
+            for (int d = 0; d < 8; d++) f[d] = p.Y[d][i];
+        }
     } else {
 #pragma unroll
         for (int d = 0; d < 8; d++) {
@@ -75,9 +94,14 @@ __global__ void __launch_bounds__(128) step_scalar_kernel(const StepParams p)
 #pragma unroll
     for (int d = 0; d < 8; d++) p.Y[d][i] = f[d];
     if (MOM) {
-        p.mx[i] = mx;
-        p.my[i] = my;
-        p.rho[i] = rho;
+        if (lazy_barrier) {  // the chain kernel already stored this cell's moments
+            mx = p.mx[i];
+            my = p.my[i];
+        } else {
+            p.mx[i] = mx;
+            p.my[i] = my;
+            p.rho[i] = rho;
+        }
     }
     // mirror the cells a neighbouring slab gathers from into its halo rows (NVLink stores)
     if (r == 0 && p.push.up_n) {
@@ -128,6 +152,11 @@ cudaError_t launch_step_scalar(const StepParams &p, int mode, bool mom, cudaStre
 // per-cell fix-up path after the vector loads.
 // ------------------------------------------------------------------------------------------------
 constexpr int V4_ROWS = 8;
+
+__device__ __forceinline__ float sel4(const float4 v, const int q)
+{
+    return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
+}
 
 template <bool MOM>
 __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParams p)
@@ -185,21 +214,20 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
     g[0][D_NW] = vnw.y; g[1][D_NW] = vnw.z; g[2][D_NW] = vnw.w; g[3][D_NW] = rnw;
     g[0][D_SW] = vsw.y; g[1][D_SW] = vsw.z; g[2][D_SW] = vsw.w; g[3][D_SW] = rsw;
 
-    const uint32_t cany = (uint32_t)c4.x | c4.y | c4.z | c4.w;
+    const uint32_t c0 = c4.x, c1 = c4.y, c2 = c4.z, c3 = c4.w;
+    const uint32_t cany = c0 | c1 | c2 | c3;
     const bool ragged = x4 + 4 > W - 1;  // group holds column W-1 or cells beyond the row end
     if (cany != 0 || ragged) {
-        const uint16_t cc[4] = {c4.x, c4.y, c4.z, c4.w};
-        if (cany & CLS_SKIP) {
+        const bool o0 = reloads_own(c0), o1 = reloads_own(c1), o2 = reloads_own(c2), o3 = reloads_own(c3);
+        if (o0 | o1 | o2 | o3) {
             // skipped cells continue from their own stale copy in the destination buffer
-            float4 o[8];
-#pragma unroll
-            for (int d = 0; d < 8; d++) o[d] = ldg4(p.Y[d] + i);
 #pragma unroll
             for (int d = 0; d < 8; d++) {
-                if (cc[0] & CLS_SKIP) g[0][d] = o[d].x;
-                if (cc[1] & CLS_SKIP) g[1][d] = o[d].y;
-                if (cc[2] & CLS_SKIP) g[2][d] = o[d].z;
-                if (cc[3] & CLS_SKIP) g[3][d] = o[d].w;
+                const float4 o = ldg4(p.Y[d] + i);
+                if (o0) g[0][d] = o.x;
+                if (o1) g[1][d] = o.y;
+                if (o2) g[2][d] = o.z;
+                if (o3) g[3][d] = o.w;
             }
         }
         if (cany & 0x3fcu) {
@@ -207,30 +235,33 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
             // cell's own opposite population
 #pragma unroll
             for (int d = 0; d < 8; d++) {
-                const uint16_t bit = cls_upstream_bit(d);
+                const uint32_t bit = cls_upstream_bit(d);
                 if (cany & bit) {
                     float4 own;
                     if (dir_opp(d) == D_E) own = ve;
                     else if (dir_opp(d) == D_W) own = vw;
                     else own = ldg4(p.X[dir_opp(d)] + i);
-                    if ((cc[0] & (bit | CLS_SKIP)) == bit) g[0][d] = own.x;
-                    if ((cc[1] & (bit | CLS_SKIP)) == bit) g[1][d] = own.y;
-                    if ((cc[2] & (bit | CLS_SKIP)) == bit) g[2][d] = own.z;
-                    if ((cc[3] & (bit | CLS_SKIP)) == bit) g[3][d] = own.w;
+                    if ((c0 & (bit | CLS_SKIP)) == bit) g[0][d] = own.x;
+                    if ((c1 & (bit | CLS_SKIP)) == bit) g[1][d] = own.y;
+                    if ((c2 & (bit | CLS_SKIP)) == bit) g[2][d] = own.z;
+                    if ((c3 & (bit | CLS_SKIP)) == bit) g[3][d] = own.w;
                 }
             }
         }
         if (ragged) {
             const uint32_t j = W - 1 - x4;  // position of column W-1 inside the group (0..3), if present
-            if (j < 4 && !(cc[j] & CLS_SKIP)) {
-                const size_t ij = i + j;
+            if (j < 4) {
+                const uint32_t cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+                if (!(cj & CLS_SKIP)) {
+                    const size_t ij = i + j;
 #pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    if (dir_dx(d) < 0 && !(cc[j] & cls_upstream_bit(d))) {
-                        const float v = p.X[d][pull_src(ij, W - 1, d, W, P)];
+                    for (int d = 0; d < 8; d++) {
+                        if (dir_dx(d) < 0 && !(cj & cls_upstream_bit(d))) {
+                            const float v = p.X[d][pull_src(ij, W - 1, d, W, P)];
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (q == (int)j) g[q][d] = v;
+                            for (int q = 0; q < 4; q++)
+                                if (q == (int)j) g[q][d] = v;
+                        }
                     }
                 }
             }
@@ -247,6 +278,14 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
 #pragma unroll
     for (int d = 0; d < 8; d++) stg4(p.Y[d] + i, make_float4(g[0][d], g[1][d], g[2][d], g[3][d]));
     if (MOM) {
+        if (cany & CLS_CHAIN) {
+            // keep the moments the barrier-chain kernel stored at chain cells
+            const float4 ex = ldg4(p.mx + i), ey = ldg4(p.my + i), er = ldg4(p.rho + i);
+            if (c0 & CLS_CHAIN) { mx[0] = ex.x; my[0] = ey.x; rho[0] = er.x; }
+            if (c1 & CLS_CHAIN) { mx[1] = ex.y; my[1] = ey.y; rho[1] = er.y; }
+            if (c2 & CLS_CHAIN) { mx[2] = ex.z; my[2] = ey.z; rho[2] = er.z; }
+            if (c3 & CLS_CHAIN) { mx[3] = ex.w; my[3] = ey.w; rho[3] = er.w; }
+        }
         stg4(p.mx + i, make_float4(mx[0], mx[1], mx[2], mx[3]));
         stg4(p.my + i, make_float4(my[0], my[1], my[2], my[3]));
         stg4(p.rho + i, make_float4(rho[0], rho[1], rho[2], rho[3]));

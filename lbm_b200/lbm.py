@@ -112,6 +112,8 @@ PROTOTYPES = {
     "blbm_exchange_halos": (_I, [_P]),
     "blbm_set_kernel": (_I, [_P, _I]),
     "blbm_get_kernel": (_I, [_P]),
+    "blbm_set_lazy_barriers": (_I, [_P, _I]),
+    "blbm_get_lazy_barriers_active": (_I, [_P]),
     "blbm_get_launch_count": (_U64, [_P]),
     "blbm_get_device_bytes": (_U64, [_P]),
 }
@@ -142,7 +144,7 @@ def _check(rc):
 class LBM:
     """One slab of a D2Q9 BGK lattice on one B200 (the whole lattice unless `rows` is given)."""
 
-    def __init__(self, omega, x, y, inflow_ux=0.1, device=0, rows=None, kernel=Kernel.Auto):
+    def __init__(self, omega, x, y, inflow_ux=0.1, device=0, rows=None, kernel=Kernel.Auto, lazy_barriers=None):
         self._L = load_library()
         self._h = _P()
         self.x, self.y = int(x), int(y)
@@ -155,6 +157,8 @@ class LBM:
         self.summary_stat = SummaryStat.Curl
         if kernel != Kernel.Auto:
             self.set_kernel(kernel)
+        if lazy_barriers is not None:
+            self.set_lazy_barriers(lazy_barriers)
 
     # -- life cycle
     def close(self):
@@ -329,6 +333,13 @@ class LBM:
     def get_kernel(self):
         return Kernel(self._L.blbm_get_kernel(self._h))
 
+    def set_lazy_barriers(self, mode):
+        """0 never, 1 always, 2 auto: keep barrier cells in the compact chain table (bit-identical)."""
+        _check(self._L.blbm_set_lazy_barriers(self._h, int(mode)))
+
+    def lazy_barriers_active(self):
+        return bool(self._L.blbm_get_lazy_barriers_active(self._h))
+
     def launch_count(self):
         return int(self._L.blbm_get_launch_count(self._h))
 
@@ -352,10 +363,10 @@ class SlabGroup:
     as `LBM`.  (One-process-per-GPU deployments link `LBM(rows=...)` slabs with export_peer/link_peer
     instead; see bench.py.)"""
 
-    def __init__(self, omega, x, y, devices, inflow_ux=0.1, kernel=Kernel.Auto):
+    def __init__(self, omega, x, y, devices, inflow_ux=0.1, kernel=Kernel.Auto, lazy_barriers=None):
         self.x, self.y = int(x), int(y)
         self.ranges = slab_rows(y, len(devices))
-        self.slabs = [LBM(omega, x, y, inflow_ux, dev, rows=r, kernel=kernel)
+        self.slabs = [LBM(omega, x, y, inflow_ux, dev, rows=r, kernel=kernel, lazy_barriers=lazy_barriers)
                       for dev, r in zip(devices, self.ranges)]
         L = load_library()
         for up, lo in zip(self.slabs[:-1], self.slabs[1:]):
