@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--workload", default="porous16384", choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", default="auto", choices=["auto", "scalar", "vec4", "tma"])
     ap.add_argument("--frame-steps", type=int, default=15, help="steps per frame of the e2e loop (lib.rs:17)")
+    ap.add_argument("--block-rows", type=int, default=0, help="vec4 kernel rows per block (4, 8, 16); 0 = default")
+    ap.add_argument("--lazy", type=int, default=-1, help="barrier-chain table: 0 never, 1 always, 2 auto (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -231,7 +233,10 @@ def main():
     h_total = rows_gpu * world
     r0, r1 = rank * rows_gpu, (rank + 1) * rows_gpu
     kernel = {"auto": Kernel.Auto, "scalar": Kernel.Scalar, "vec4": Kernel.Vec4, "tma": Kernel.Tma}[args.kernel]
-    lbm = LBM(omega, w, h_total, inflow_ux=u0, device=local, rows=(r0, r1), kernel=kernel)
+    lbm = LBM(omega, w, h_total, inflow_ux=u0, device=local, rows=(r0, r1), kernel=kernel,
+              lazy_barriers=None if args.lazy < 0 else args.lazy)
+    if args.block_rows:
+        lbm.set_tuning(0, args.block_rows)
     if world > 1:
         blobs = [None] * world
         dist.all_gather_object(blobs, lbm.export_peer())

@@ -198,6 +198,9 @@ int blbm_exchange_halos(blbm_t *h);
 /* ---- tuning / measurement -------------------------------------------------------------------- */
 int blbm_set_kernel(blbm_t *h, int kernel); /* blbm_kernel */
 int blbm_get_kernel(const blbm_t *h);       /* the resolved implementation (never AUTO) */
+/* launch-shape knobs for A/B measurement; results never depend on them */
+typedef enum blbm_tune { BLBM_TUNE_VEC4_BLOCK_ROWS = 0 /* 4, 8 (default) or 16 rows of 128 cells per block */ } blbm_tune;
+int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale
  * copies; the collision shaders have no mask test), so their state can live in a compact side table that is advanced in
  * registers, which removes their memory traffic from the step kernel.  Results are bit-identical either

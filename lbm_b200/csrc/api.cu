@@ -91,6 +91,7 @@ struct blbm {
     float *f[2][8] = {};
     float *R = nullptr, *mx = nullptr, *my = nullptr, *rho = nullptr, *out = nullptr;
     uint16_t *cls[2] = {};
+    uint8_t *rowflag[2] = {};  // per class buffer: one byte per (row, 128-cell chunk), see build_class_kernel
     uint8_t *mask = nullptr;
     unsigned long long *flags = nullptr;  // [0] epoch from the slab above, [16] from below (128 B apart)
     int *err_flag = nullptr;
@@ -100,12 +101,15 @@ struct blbm {
     size_t off_mx = 0, off_my = 0, off_flags = 0;
     int cls_cur = 0;
     bool cls_pending = false;  // the mask changed while a stream was pending: cls[cls_cur^1] is newer
+    // owned rows in which the two class buffers may differ (a paint rebuilds only the rows it touches)
+    uint32_t diff_lo = 0, diff_hi = 0;
     bool regimeT = false;
     bool halo_dirty = false;
     float omega = 1.0f;
     int stat = BLBM_CURL;
     uint64_t step = 0, frame = 0;
     int kernel = BLBM_KERNEL_VEC4;
+    int vec4_rows = 4;  // rows per block of the vec4 kernel (tuning knob; 4 measured best on the porous case)
     uint64_t launches = 0;
     Peer up, dn;
     unsigned long long epoch = 0, waited = 0;
@@ -120,6 +124,7 @@ struct blbm {
     float *chain_state = nullptr;
     size_t chain_n = 0, chain_cap = 0;
     unsigned long long *chain_counter = nullptr;
+    unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
 };
 
 namespace {
@@ -236,11 +241,10 @@ int chain_try_enter(blbm *h, uint32_t steps_left)
     if (h->chain_active || h->lazy_mode == 0 || h->chain_declined || h->cls_pending) return BLBM_OK;
     if (h->lazy_mode == 2 && steps_left < 8) return BLBM_OK;
     if (h->plane >= 0xffffffffull) return BLBM_OK;
-    CK(launch_chain_count(h->cls[h->cls_cur], geom(h), h->chain_counter, h->stream));
-    h->launches++;
-    unsigned long long n = 0;
-    CK(cudaMemcpyAsync(&n, h->chain_counter, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+    CK(launch_chain_count(h->cls[h->cls_cur], geom(h), h->chain_counter, h->mailbox_dev, h->stream));
+    h->launches += 2;
     CK(cudaStreamSynchronize(h->stream));
+    const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(h->mailbox_host);
     const unsigned long long cells = (unsigned long long)h->rows * h->W;
     if (n == 0 || (h->lazy_mode == 2 && n * 50ull < cells)) {
         h->chain_declined = true;
@@ -262,8 +266,8 @@ int chain_try_enter(blbm *h, uint32_t steps_left)
         }
         h->chain_cap = (size_t)n;
     }
-    CK(launch_chain_build(h->cls[h->cls_cur], geom(h), chain_planes(h), h->chain_idx, h->chain_state, h->chain_cap,
-                          h->chain_counter, h->stream));
+    CK(launch_chain_build(h->cls[h->cls_cur], h->cls[h->cls_cur ^ 1], geom(h), chain_planes(h), h->chain_idx,
+                          h->chain_state, h->chain_cap, h->chain_counter, h->stream));
     h->launches++;
     h->chain_n = (size_t)n;
     h->chain_active = true;
@@ -280,6 +284,7 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     }
     p.R = h->R;
     p.cls = h->cls[h->cls_cur];
+    p.rowflag = h->rowflag[h->cls_cur];
     p.mx = h->mx;
     p.my = h->my;
     p.rho = h->rho;
@@ -300,7 +305,7 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     cudaError_t e;
     switch (k) {
     case BLBM_KERNEL_SCALAR: e = launch_step_scalar(p, mode, mom, h->stream); break;
-    default: e = launch_step_vec4(p, mode, mom, h->stream); break;
+    default: e = launch_step_vec4(p, mode, mom, h->vec4_rows, h->stream); break;
     }
     if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -373,15 +378,34 @@ int do_steps(blbm *h, uint32_t n)
     return BLBM_OK;
 }
 
-int rebuild_class(blbm *h)
+// The mask changed in owned rows [lo, hi): bring the class words (and chunk flags) up to date.
+// big_change: the number of barrier cells may have changed enough for auto mode to decide afresh.
+int rebuild_class(blbm *h, uint32_t lo, uint32_t hi, bool big_change)
 {
-    h->chain_declined = false;  // new mask: auto mode decides afresh (callers flushed the table already)
-    // in the T-regime the pending stream must still see the old classification
-    const int target = h->regimeT ? (h->cls_cur ^ 1) : h->cls_cur;
+    if (big_change) h->chain_declined = false;
+    if (hi > h->rows) hi = h->rows;
+    if (lo >= hi) return BLBM_OK;
+    const bool had_diff = h->diff_hi > h->diff_lo;
+    const uint32_t ulo = had_diff ? std::min(lo, h->diff_lo) : lo, uhi = had_diff ? std::max(hi, h->diff_hi) : hi;
+    int target;
+    uint32_t blo = lo, bhi = hi;
+    if (h->regimeT) {
+        // the pending stream must still see the old classification: build the other buffer; unless a newer
+        // classification is already waiting there, that buffer is also stale wherever the two differ
+        target = h->cls_cur ^ 1;
+        if (!h->cls_pending) {
+            blo = ulo;
+            bhi = uhi;
+        }
+        h->cls_pending = true;
+    } else {
+        target = h->cls_cur;
+    }
+    h->diff_lo = ulo;
+    h->diff_hi = uhi;
     CK(launch_build_class(h->cls[target], h->mask, geom(h), h->chain_active ? h->cls[h->cls_cur] : nullptr,
-                          h->stream));
+                          h->rowflag[target], blo, bhi, h->stream));
     h->launches++;
-    if (h->regimeT) h->cls_pending = true;
     return BLBM_OK;
 }
 
@@ -648,6 +672,8 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     h->off_my = carve(pb);
     const size_t off_rho = carve(pb), off_out = carve(pb);
     const size_t off_cls0 = carve(h->plane * sizeof(uint16_t)), off_cls1 = carve(h->plane * sizeof(uint16_t));
+    const size_t flag_bytes = (size_t)h->rows * ((h->P + CHUNK - 1) / CHUNK);
+    const size_t off_rf0 = carve(flag_bytes), off_rf1 = carve(flag_bytes);
     const size_t off_mask = carve((size_t)(h->rows + 4) * h->P);
     h->off_flags = carve(256);
     const size_t off_err = carve(64), off_red = carve(64), off_cnt = carve(64);
@@ -666,6 +692,8 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     h->out = reinterpret_cast<float *>(h->pool + off_out);
     h->cls[0] = reinterpret_cast<uint16_t *>(h->pool + off_cls0);
     h->cls[1] = reinterpret_cast<uint16_t *>(h->pool + off_cls1);
+    h->rowflag[0] = reinterpret_cast<uint8_t *>(h->pool + off_rf0);
+    h->rowflag[1] = reinterpret_cast<uint8_t *>(h->pool + off_rf1);
     h->mask = reinterpret_cast<uint8_t *>(h->pool + off_mask);
     h->flags = reinterpret_cast<unsigned long long *>(h->pool + h->off_flags);
     h->err_flag = reinterpret_cast<int *>(h->pool + off_err);
@@ -676,7 +704,9 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     int rc = BLBM_OK;
     do {
         cudaError_t ce;
-        if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        if ((ce = cudaHostAlloc((void **)&h->mailbox_host, 64, cudaHostAllocMapped)) != cudaSuccess ||
+            (ce = cudaHostGetDevicePointer((void **)&h->mailbox_dev, h->mailbox_host, 0)) != cudaSuccess ||
+            (ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
             (ce = cudaEventCreateWithFlags(&h->ev_sum, cudaEventDisableTiming)) != cudaSuccess ||
@@ -687,7 +717,10 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
         }
         if ((rc = fill_equilibrium(h, inflow_ux, -1)) != BLBM_OK) break;
         if ((ce = launch_mask_init(h->mask, geom(h), h->stream)) != cudaSuccess ||
-            (ce = launch_build_class(h->cls[0], h->mask, geom(h), nullptr, h->stream)) != cudaSuccess) {
+            (ce = launch_build_class(h->cls[0], h->mask, geom(h), nullptr, h->rowflag[0], 0, h->rows, h->stream)) !=
+                cudaSuccess ||
+            (ce = launch_build_class(h->cls[1], h->mask, geom(h), nullptr, h->rowflag[1], 0, h->rows, h->stream)) !=
+                cudaSuccess) {
             rc = fail(BLBM_ECUDA, "mask setup failed: %s", cudaGetErrorString(ce));
             break;
         }
@@ -723,6 +756,7 @@ int blbm_destroy(blbm_t *h)
         stream_free(h->chain_state, h->stream);
         cudaStreamSynchronize(h->stream);
     }
+    if (h->mailbox_host) cudaFreeHost(h->mailbox_host);
     if (h->pool) cudaFree(h->pool);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
@@ -891,6 +925,15 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         uniq.push_back(pairs[2 * idx[q].second + 1]);
     }
     const size_t nu = uniq.size() / 2;
+    // owned rows whose class words depend on the painted cells: a cell at row y is an upstream neighbour of
+    // rows y-1..y+1, and through the flat-index wrap of column W-1 also of row y-2
+    uint32_t rlo = 0, rhi = 0;
+    if (nu) {
+        const int64_t ymin = (int64_t)(uniq[0] / h->W) - (int64_t)h->row0;           // uniq is sorted by location
+        const int64_t ymax = (int64_t)(uniq[2 * (nu - 1)] / h->W) - (int64_t)h->row0;
+        rlo = (uint32_t)std::max<int64_t>(0, ymin - 2);
+        rhi = (uint32_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)h->rows, ymax + 3));
+    }
     if (nu) {
         if (h->d_pairs_cap < nu) {
             stream_free(h->d_pairs, h->stream);
@@ -912,8 +955,7 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         h->launches++;
         CK(cudaStreamSynchronize(h->stream));  // uniq is pageable host memory owned by this frame
     }
-    // every slab rebuilds, whether or not a point landed here: keeps launch sequences identical
-    return rebuild_class(h);
+    return rebuild_class(h, rlo, rhi, nu * 100ull >= (unsigned long long)h->rows * h->W);
 }
 
 int blbm_draw_points(blbm_t *h, const uint32_t *pairs, size_t npairs)
@@ -940,7 +982,7 @@ int blbm_reset_barrier(blbm_t *h)
     }
     CK(launch_mask_init(h->mask, geom(h), h->stream));
     h->launches++;
-    return rebuild_class(h);
+    return rebuild_class(h, 0, h->rows, true);
 }
 
 int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const uint8_t *mask)
@@ -962,7 +1004,7 @@ int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const
                              h->W, (size_t)(hi - lo), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));  // the caller's buffer is free again on return
     }
-    return rebuild_class(h);
+    return rebuild_class(h, 0, h->rows, true);
 }
 
 uint64_t blbm_get_compute_num(const blbm_t *h) { return h ? h->step : 0; }
@@ -1075,14 +1117,19 @@ int blbm_read_cell_class(blbm_t *h, uint16_t *dst)
 {
     CKH(h);
     if (!dst) return fail(BLBM_EINVAL, "dst is null");
-    const uint16_t *c = h->cls[h->cls_pending ? (h->cls_cur ^ 1) : h->cls_cur];  // class of the current mask
-    CK(cudaMemcpy2DAsync(dst, (size_t)h->W * 2, c + row_off(0, h->P), (size_t)h->P * 2, (size_t)h->W * 2, h->rows,
-                         cudaMemcpyDeviceToHost, h->stream));
-    int rc = sync_stream(h);
-    if (rc) return rc;
-    const size_t ncell = (size_t)h->rows * h->W;
-    for (size_t q = 0; q < ncell; q++) dst[q] &= CLS_PUBLIC;  // drop the internal chain-table bits
-    return BLBM_OK;
+    // the kernel-facing class words use an internal encoding; the public word is derived from the (current)
+    // mask on demand
+    const size_t bytes = (size_t)h->rows * h->W * sizeof(uint16_t);
+    uint16_t *tmp = nullptr;
+    if (stream_alloc((void **)&tmp, bytes, h->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BLBM_ENOMEM, "allocating %zu bytes for the class read-back failed", bytes);
+    }
+    CK(launch_build_public_class(tmp, h->mask, geom(h), h->stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, h->stream));
+    stream_free(tmp, h->stream);
+    return sync_stream(h);
 }
 
 int blbm_reduce_moments(blbm_t *h, double *sum_rho, double *sum_mx, double *sum_my, float *max_abs_output)
@@ -1198,6 +1245,19 @@ int blbm_set_kernel(blbm_t *h, int kernel)
 }
 
 int blbm_get_kernel(const blbm_t *h) { return h ? h->kernel : BLBM_EINVAL; }
+
+int blbm_set_tuning(blbm_t *h, int knob, int value)
+{
+    if (!h) return fail(BLBM_EINVAL, "null handle");
+    switch (knob) {
+    case BLBM_TUNE_VEC4_BLOCK_ROWS:
+        if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(BLBM_EINVAL, "block rows must be 1, 2, 4, 8 or 16");
+        h->vec4_rows = value;
+        return BLBM_OK;
+    default: return fail(BLBM_EINVAL, "unknown tuning knob %d", knob);
+    }
+}
 
 int blbm_set_lazy_barriers(blbm_t *h, int mode)
 {

@@ -115,34 +115,76 @@ __device__ __forceinline__ uint32_t mask_at(const uint8_t *mask, const SlabGeom 
     return mask[mask_row_off(lr, g.P) + (size_t)gx];
 }
 
-__global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const SlabGeom g, const uint16_t *keep_chain)
+// One warp per 128-cell chunk of a row (4 cells per lane); PUBLIC selects the word of blbm_read_cell_class
+// (densely packed rows x W) instead of the kernel-facing word (plane layout) and skips the chunk flags.
+template <bool PUBLIC>
+__global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const SlabGeom g, const uint16_t *keep_chain,
+                                   uint8_t *rowflag, const uint32_t row_begin, const uint32_t row_end)
 {
-    const size_t total = (size_t)g.rows * g.P;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(t / g.P);
-        const uint32_t x = (uint32_t)(t - (size_t)r * g.P);
-        uint16_t c = 0;
-        if (x < g.W) {
-            const int64_t gy = (int64_t)g.row0 + r;
-            const bool bar = mask[mask_row_off(r, g.P) + x] == 1;
-            if (bar) c |= CLS_BARRIER;
-            if (bar || x == 0 || gy >= (int64_t)g.Hg - 1) c |= CLS_SKIP;
+    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
+    const size_t nwarps_total = (size_t)(row_end - row_begin) * nchunk;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nwarps_total;
+         wid += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        const uint32_t r = row_begin + (uint32_t)(wid / nchunk);
+        const uint32_t chunk = (uint32_t)(wid % nchunk);
+        const int64_t gy = (int64_t)g.row0 + r;
+        uint32_t any = 0;
 #pragma unroll
-            for (int d = 0; d < 8; d++)
-                if (mask_at(mask, g, (int64_t)x - dir_dx(d), gy - dir_dy(d)) == 1) c |= cls_upstream_bit(d);
-            // cells whose state lives in the chain table stay there (a paint evicts the cells it touches
-            // before the mask changes, so a kept bit always belongs to a cell that is still a barrier)
-            if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & CLS_CHAIN;
+        for (int q = 0; q < 4; q++) {
+            const uint32_t x = chunk * CHUNK + lane * 4u + q;
+            if (x >= g.P) continue;
+            uint16_t c = 0;
+            if (x < g.W) {
+                const bool bar = mask[mask_row_off(r, g.P) + x] == 1;
+                const bool skip = bar || x == 0 || gy >= (int64_t)g.Hg - 1;
+                uint32_t up = 0;
+#pragma unroll
+                for (int d = 0; d < 8; d++)
+                    if (mask_at(mask, g, (int64_t)x - dir_dx(d), gy - dir_dy(d)) == 1) up |= 1u << d;
+                if (PUBLIC) {
+                    c = (uint16_t)((bar ? PUB_BARRIER : 0) | (skip ? PUB_SKIP : 0) | (up << 2));
+                } else {
+                    c = (uint16_t)((bar ? CLS_BARRIER : 0) | (skip ? CLS_SKIP : (uint16_t)up));
+                    // cells whose state lives in the chain table stay there (a paint evicts the cells it
+                    // touches before the mask changes, so a kept bit belongs to a cell that is still a barrier)
+                    if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & CLS_CHAIN;
+                }
+            }
+            if (PUBLIC) {
+                if (x < g.W) cls[(size_t)r * g.W + x] = c;
+            } else {
+                cls[row_off(r, g.P) + x] = c;
+                any |= c;
+            }
         }
-        cls[row_off(r, g.P) + x] = c;
+        if (!PUBLIC && rowflag) {
+            any = __reduce_or_sync(0xffffffffu, any);
+            if (lane == 0) rowflag[(size_t)r * nchunk + chunk] = any ? 1 : 0;
+        }
     }
 }
 
-cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, const uint16_t *keep_chain,
-                               cudaStream_t st)
+static unsigned class_grid(const SlabGeom &g, uint32_t nrows)
 {
-    build_class_kernel<<<148 * 8, 256, 0, st>>>(cls, mask, g, keep_chain);
+    const size_t warps = (size_t)nrows * ((g.P + CHUNK - 1) / CHUNK);
+    size_t nb = (warps + 7) / 8;  // 8 warps per block
+    if (nb > 148 * 8) nb = 148 * 8;
+    return (unsigned)(nb ? nb : 1);
+}
+
+cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, const uint16_t *keep_chain,
+                               uint8_t *rowflag, uint32_t row_begin, uint32_t row_end, cudaStream_t st)
+{
+    if (row_end <= row_begin) return cudaSuccess;
+    build_class_kernel<false><<<class_grid(g, row_end - row_begin), 256, 0, st>>>(cls, mask, g, keep_chain, rowflag,
+                                                                                  row_begin, row_end);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_public_class(uint16_t *dst, const uint8_t *mask, const SlabGeom &g, cudaStream_t st)
+{
+    build_class_kernel<true><<<class_grid(g, g.rows), 256, 0, st>>>(dst, mask, g, nullptr, nullptr, 0, g.rows);
     return cudaGetLastError();
 }
 
@@ -385,17 +427,26 @@ __global__ void chain_count_kernel(const uint16_t *cls, const SlabGeom g, unsign
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
 
+__global__ void mailbox_kernel(unsigned long long *host_mapped, const unsigned long long *src)
+{
+    *host_mapped = *src;
+    __threadfence_system();
+}
+
+// host_mailbox: mapped pinned host word the result is posted to by a store from the GPU — a D2H memcpy
+// would queue behind a large asynchronous read-back on the same copy engine
 cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, unsigned long long *count,
-                               cudaStream_t st)
+                               unsigned long long *host_mailbox, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     chain_count_kernel<<<148 * 8, 256, 0, st>>>(cls, g, count);
+    mailbox_kernel<<<1, 1, 0, st>>>(host_mailbox, count);
     return cudaGetLastError();
 }
 
-__global__ void chain_build_kernel(uint16_t *cls, const SlabGeom g, const ChainPlanes pl, uint32_t *idx,
-                                   float *state, size_t cap, unsigned long long *cursor)
+__global__ void chain_build_kernel(uint16_t *cls, uint16_t *cls_other, const SlabGeom g, const ChainPlanes pl,
+                                   uint32_t *idx, float *state, size_t cap, unsigned long long *cursor)
 {
     const size_t total = (size_t)g.rows * g.P;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -406,6 +457,7 @@ __global__ void chain_build_kernel(uint16_t *cls, const SlabGeom g, const ChainP
         const size_t e = (size_t)atomicAdd(cursor, 1ull);
         if (e >= cap) continue;
         cls[i] = c | CLS_CHAIN;
+        cls_other[i] |= CLS_CHAIN;  // the other class buffer may be stale elsewhere, but never about this bit
         idx[e] = (uint32_t)i;
 #pragma unroll
         for (int d = 0; d < 8; d++) {
@@ -416,12 +468,12 @@ __global__ void chain_build_kernel(uint16_t *cls, const SlabGeom g, const ChainP
     }
 }
 
-cudaError_t launch_chain_build(uint16_t *cls, const SlabGeom &g, const ChainPlanes &pl, uint32_t *idx,
-                               float *state, size_t cap, unsigned long long *cursor, cudaStream_t st)
+cudaError_t launch_chain_build(uint16_t *cls, uint16_t *cls_other, const SlabGeom &g, const ChainPlanes &pl,
+                               uint32_t *idx, float *state, size_t cap, unsigned long long *cursor, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    chain_build_kernel<<<148 * 8, 256, 0, st>>>(cls, g, pl, idx, state, cap, cursor);
+    chain_build_kernel<<<148 * 8, 256, 0, st>>>(cls, cls_other, g, pl, idx, state, cap, cursor);
     return cudaGetLastError();
 }
 

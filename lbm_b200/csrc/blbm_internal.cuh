@@ -19,16 +19,26 @@ __host__ __device__ constexpr int dir_dx(int d) { return d == D_NW || d == D_W |
 __host__ __device__ constexpr int dir_dy(int d) { return d <= D_NE ? -1 : (d <= D_E ? 0 : 1); }
 __host__ __device__ constexpr int dir_opp(int d) { return 7 - d; }
 
-// class word per cell (also what blbm_read_cell_class returns)
-constexpr uint16_t CLS_BARRIER = 1u;
-constexpr uint16_t CLS_SKIP = 2u;
-// internal bits, masked out of blbm_read_cell_class: the cell's state lives in the barrier-chain table
-// (its plane slots are don't-care), and a scratch mark used while a paint evicts cells from that table
-constexpr uint16_t CLS_CHAIN = 1u << 10;
+// Internal class word per cell, laid out for the step kernel (the public word of blbm_read_cell_class —
+// bit0 barrier, bit1 skipped, bits 2..9 upstream-is-barrier — is derived from the mask on demand):
+//   bits 0..7  upstream neighbour of population d is a barrier -> bounce back; ZERO for skipped cells,
+//              so the step kernel tests one bit per (cell, direction)
+//   bit 8      skipped by stream (barrier | x == 0 | y >= H-1)
+//   bit 9      state lives in the barrier-chain table; plane slots are don't-care
+//   bit 10     barrier
+//   bit 11     scratch mark while a paint evicts cells from the chain table
+constexpr uint16_t CLS_UP_MASK = 0xffu;
+constexpr uint16_t CLS_SKIP = 1u << 8;
+constexpr uint16_t CLS_CHAIN = 1u << 9;
+constexpr uint16_t CLS_BARRIER = 1u << 10;
 constexpr uint16_t CLS_DIRTY = 1u << 11;
-constexpr uint16_t CLS_PUBLIC = 0x3ffu;
 constexpr uint32_t CHAIN_DEAD = 0xffffffffu;
-__host__ __device__ constexpr uint16_t cls_upstream_bit(int d) { return (uint16_t)(4u << d); }
+__host__ __device__ constexpr uint16_t cls_upstream_bit(int d) { return (uint16_t)(1u << d); }
+// public word (blbm.h)
+constexpr uint16_t PUB_BARRIER = 1u, PUB_SKIP = 2u;
+__host__ __device__ constexpr uint16_t pub_upstream_bit(int d) { return (uint16_t)(4u << d); }
+// cells per row-chunk flag: one byte per 128 cells of a row says "some class word here is non-zero"
+constexpr uint32_t CHUNK = 128;
 
 // Where the cells that a neighbouring slab gathers from get mirrored (direct stores into the peer
 // GPU's halo rows).  Pointers address x = 0 of the destination row; null = no neighbour on that side.
@@ -48,6 +58,7 @@ struct StepParams {
     float *Y[8];        // destination buffer
     float *R;           // rest population (single array, read-modify-write)
     const uint16_t *cls;
+    const uint8_t *rowflag;  // [rows][ceil(P/128)]: 0 = every class word of that 128-cell chunk is 0
     float *mx, *my, *rho;
     uint32_t W;       // cells per row
     uint32_t P;       // row pitch in elements (multiple of 32)
@@ -135,7 +146,7 @@ enum StepMode { MODE_FUSED = 0, MODE_COLLIDE_ONLY = 1, MODE_STREAM_ONLY = 2 };
 
 // launchers (kernels.cu)
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
-cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
+cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, cudaStream_t st);
 
 // ---- auxiliary kernels (aux_kernels.cu) ----------------------------------------------------------
 // Slab geometry shared by the auxiliary launchers.  Population/moment/class planes have rows+3 device
@@ -152,9 +163,13 @@ cudaError_t launch_fill_rows(float *const *planes, const float *values, int npla
 cudaError_t launch_mask_init(uint8_t *mask, const SlabGeom &g, cudaStream_t st);
 cudaError_t launch_mask_scatter(uint8_t *mask, const SlabGeom &g, const uint64_t *pairs, size_t npairs,
                                 cudaStream_t st);
-// keep_chain (may alias cls, may be null): class words whose CLS_CHAIN bit is carried over
+// keep_chain (may alias cls, may be null): class words whose CLS_CHAIN bit is carried over.
+// rowflag (may be null): the per-chunk "any non-zero class word" bytes are rebuilt alongside.
+// Only owned rows [row_begin, row_end) are rebuilt (a paint touches a few rows).
 cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, const uint16_t *keep_chain,
-                               cudaStream_t st);
+                               uint8_t *rowflag, uint32_t row_begin, uint32_t row_end, cudaStream_t st);
+// the public class words of blbm_read_cell_class, densely packed rows x W
+cudaError_t launch_build_public_class(uint16_t *dst, const uint8_t *mask, const SlabGeom &g, cudaStream_t st);
 cudaError_t launch_precollision_moments(const float *const *f8, float *mx, float *my, float *rho, uint32_t W,
                                         uint32_t P, uint32_t dev_row_begin, uint32_t dev_row_end,
                                         cudaStream_t st);
@@ -167,9 +182,9 @@ struct ChainPlanes {
     float *f0[8], *f1[8], *R;
 };
 cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, unsigned long long *count,
-                               cudaStream_t st);
-cudaError_t launch_chain_build(uint16_t *cls, const SlabGeom &g, const ChainPlanes &pl, uint32_t *idx,
-                               float *state, size_t cap, unsigned long long *cursor, cudaStream_t st);
+                               unsigned long long *host_mailbox, cudaStream_t st);
+cudaError_t launch_chain_build(uint16_t *cls, uint16_t *cls_other, const SlabGeom &g, const ChainPlanes &pl,
+                               uint32_t *idx, float *state, size_t cap, unsigned long long *cursor, cudaStream_t st);
 cudaError_t launch_chain_flush(const uint32_t *idx, const float *state, size_t n, size_t cap,
                                const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1, cudaStream_t st);
 // a paint is about to change the mask at `pairs` (global location, value): move those cells' chains back

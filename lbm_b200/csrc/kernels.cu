@@ -151,14 +151,14 @@ cudaError_t launch_step_scalar(const StepParams &p, int mode, bool mom, cudaStre
 // Cells that need anything but a plain pull (class word != 0, column W-1, ragged row end) take a
 // per-cell fix-up path after the vector loads.
 // ------------------------------------------------------------------------------------------------
-constexpr int V4_ROWS = 8;
+// rows per block is a tuning knob (blbm_set_tuning): 4, 8 (default) or 16
 
 __device__ __forceinline__ float sel4(const float4 v, const int q)
 {
     return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
 }
 
-template <bool MOM>
+template <bool MOM, int V4_ROWS>
 __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParams p)
 {
     const uint32_t nbx = (p.P + 127u) / 128u;
@@ -176,8 +176,11 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
     ushort4 c4 = make_ushort4(0, 0, 0, 0);
     float4 vn, vs, ve, vw, vne, vnw, vse, vsw, vr;
     vn = vs = ve = vw = vne = vnw = vse = vsw = vr = make_float4(0.f, 0.f, 0.f, 0.f);
+    // one flag byte per (row, 128-cell chunk) — the same address for the whole warp — tells whether any
+    // class word of the chunk is non-zero; clean chunks never touch the class plane
+    const bool chunk_dirty = p.rowflag[(size_t)r * nbx + bx] != 0;
     if (valid) {
-        c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
+        if (chunk_dirty) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
         vn = ldg4(p.X[D_N] + i + P);
         vne = ldg4(p.X[D_NE] + i + P);
         vnw = ldg4(p.X[D_NW] + i + P);
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
                 if (o3) g[3][d] = o.w;
             }
         }
-        if (cany & 0x3fcu) {
+        if (cany & CLS_UP_MASK) {
             // half-way bounce-back: population d of a cell whose upstream neighbour is a barrier is the
             // cell's own opposite population
 #pragma unroll
@@ -241,10 +244,11 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
                     if (dir_opp(d) == D_E) own = ve;
                     else if (dir_opp(d) == D_W) own = vw;
                     else own = ldg4(p.X[dir_opp(d)] + i);
-                    if ((c0 & (bit | CLS_SKIP)) == bit) g[0][d] = own.x;
-                    if ((c1 & (bit | CLS_SKIP)) == bit) g[1][d] = own.y;
-                    if ((c2 & (bit | CLS_SKIP)) == bit) g[2][d] = own.z;
-                    if ((c3 & (bit | CLS_SKIP)) == bit) g[3][d] = own.w;
+                    // (skipped cells carry no upstream bits, so one bit test decides)
+                    if (c0 & bit) g[0][d] = own.x;
+                    if (c1 & bit) g[1][d] = own.y;
+                    if (c2 & bit) g[2][d] = own.z;
+                    if (c3 & bit) g[3][d] = own.w;
                 }
             }
         }
@@ -312,16 +316,28 @@ __global__ void __launch_bounds__(32 * V4_ROWS) step_vec4_kernel(const StepParam
     }
 }
 
-cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, cudaStream_t st)
+template <int V4_ROWS>
+static cudaError_t launch_vec4_rows(const StepParams &p, bool mom, cudaStream_t st)
 {
-    if (mode != MODE_FUSED) return launch_step_scalar(p, mode, mom, st);
     const uint32_t nbx = (p.P + 127u) / 128u;
     const uint64_t nblocks = (uint64_t)nbx * ((p.rows + V4_ROWS - 1) / V4_ROWS);
     if (nblocks == 0 || nblocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     dim3 grid((unsigned)nblocks), block(32, V4_ROWS);
-    if (mom) step_vec4_kernel<true><<<grid, block, 0, st>>>(p);
-    else step_vec4_kernel<false><<<grid, block, 0, st>>>(p);
+    if (mom) step_vec4_kernel<true, V4_ROWS><<<grid, block, 0, st>>>(p);
+    else step_vec4_kernel<false, V4_ROWS><<<grid, block, 0, st>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, int block_rows, cudaStream_t st)
+{
+    if (mode != MODE_FUSED) return launch_step_scalar(p, mode, mom, st);
+    switch (block_rows) {
+    case 1: return launch_vec4_rows<1>(p, mom, st);
+    case 2: return launch_vec4_rows<2>(p, mom, st);
+    case 4: return launch_vec4_rows<4>(p, mom, st);
+    case 16: return launch_vec4_rows<16>(p, mom, st);
+    default: return launch_vec4_rows<8>(p, mom, st);
+    }
 }
 
 }  // namespace blbmk

@@ -112,6 +112,7 @@ PROTOTYPES = {
     "blbm_exchange_halos": (_I, [_P]),
     "blbm_set_kernel": (_I, [_P, _I]),
     "blbm_get_kernel": (_I, [_P]),
+    "blbm_set_tuning": (_I, [_P, _I, _I]),
     "blbm_set_lazy_barriers": (_I, [_P, _I]),
     "blbm_get_lazy_barriers_active": (_I, [_P]),
     "blbm_get_launch_count": (_U64, [_P]),
@@ -332,6 +333,9 @@ class LBM:
 
     def get_kernel(self):
         return Kernel(self._L.blbm_get_kernel(self._h))
+
+    def set_tuning(self, knob, value):
+        _check(self._L.blbm_set_tuning(self._h, int(knob), int(value)))
 
     def set_lazy_barriers(self, mode):
         """0 never, 1 always, 2 auto: keep barrier cells in the compact chain table (bit-identical)."""
