@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "scalar", "vec4", "tma"])
     ap.add_argument("--frame-steps", type=int, default=15, help="steps per frame of the e2e loop (lib.rs:17)")
     ap.add_argument("--block-rows", type=int, default=0, help="vec4 kernel rows per block (4, 8, 16); 0 = default")
+    ap.add_argument("--tma-rows", type=int, default=0)
+    ap.add_argument("--tma-stages", type=int, default=0)
+    ap.add_argument("--tma-ctas", type=int, default=0)
     ap.add_argument("--lazy", type=int, default=-1, help="barrier-chain table: 0 never, 1 always, 2 auto (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -237,6 +240,9 @@ def main():
               lazy_barriers=None if args.lazy < 0 else args.lazy)
     if args.block_rows:
         lbm.set_tuning(0, args.block_rows)
+    for knob, val in ((1, args.tma_rows), (2, args.tma_stages), (3, args.tma_ctas)):
+        if val:
+            lbm.set_tuning(knob, val)
     if world > 1:
         blobs = [None] * world
         dist.all_gather_object(blobs, lbm.export_peer())

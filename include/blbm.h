@@ -59,7 +59,7 @@ typedef enum blbm_kernel {
     BLBM_KERNEL_AUTO = 0,
     BLBM_KERNEL_SCALAR = 1, /* one cell per thread, 32-bit accesses */
     BLBM_KERNEL_VEC4 = 2,   /* four cells per thread, 128-bit accesses, shuffle-realigned x+-1 gathers */
-    BLBM_KERNEL_TMA = 3     /* TMA (cp.async.bulk.tensor) staged tiles, mbarrier pipeline */
+    BLBM_KERNEL_TMA = 3     /* persistent CTAs, TMA (cp.async.bulk.tensor) staged tiles, mbarrier ring */
 } blbm_kernel;
 
 #define BLBM_PEER_HANDLE_BYTES 512
@@ -199,7 +199,12 @@ int blbm_exchange_halos(blbm_t *h);
 int blbm_set_kernel(blbm_t *h, int kernel); /* blbm_kernel */
 int blbm_get_kernel(const blbm_t *h);       /* the resolved implementation (never AUTO) */
 /* launch-shape knobs for A/B measurement; results never depend on them */
-typedef enum blbm_tune { BLBM_TUNE_VEC4_BLOCK_ROWS = 0 /* 4, 8 (default) or 16 rows of 128 cells per block */ } blbm_tune;
+typedef enum blbm_tune {
+    BLBM_TUNE_VEC4_BLOCK_ROWS = 0, /* rows of 128 cells per block: 1, 2, 4 (default), 8, 16 */
+    BLBM_TUNE_TMA_TILE_ROWS = 1,   /* rows per TMA tile: 4 (default) or 8 */
+    BLBM_TUNE_TMA_STAGES = 2,      /* depth of the shared-memory ring: 2..4 (default 4) */
+    BLBM_TUNE_TMA_CTAS_PER_SM = 3  /* persistent CTAs per SM: 1..8 (default 2) */
+} blbm_tune;
 int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale
  * copies; the collision shaders have no mask test), so their state can live in a compact side table that is advanced in

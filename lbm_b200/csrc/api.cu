@@ -110,6 +110,11 @@ struct blbm {
     uint64_t step = 0, frame = 0;
     int kernel = BLBM_KERNEL_VEC4;
     int vec4_rows = 4;  // rows per block of the vec4 kernel (tuning knob; 4 measured best on the porous case)
+    // TMA-staged kernel: tensor maps (opaque 128-byte descriptors) and launch shape
+    alignas(64) unsigned char tma_maps[16 * 128];
+    alignas(64) unsigned char tma_map_rest[128];
+    bool tma_ready = false;
+    int tma_rows = 4, tma_stages = 4, tma_ctas = 2;
     uint64_t launches = 0;
     Peer up, dn;
     unsigned long long epoch = 0, waited = 0;
@@ -305,6 +310,10 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     cudaError_t e;
     switch (k) {
     case BLBM_KERNEL_SCALAR: e = launch_step_scalar(p, mode, mom, h->stream); break;
+    case BLBM_KERNEL_TMA:
+        e = launch_step_tma(p, mode, mom, h->tma_maps, h->tma_map_rest, xbuf, h->tma_rows, h->tma_stages, h->tma_ctas,
+                            h->stream);
+        break;
     default: e = launch_step_vec4(p, mode, mom, h->vec4_rows, h->stream); break;
     }
     if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
@@ -1232,13 +1241,30 @@ int blbm_exchange_halos(blbm_t *h)
     return push_all_halos(h);
 }
 
+static int tma_prepare(blbm *h)
+{
+    if (!tma_available()) return fail(BLBM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    if (!tma_encode_planes(h->tma_maps, h->f, h->R, h->tma_map_rest, h->P, h->rows + 3, h->tma_rows))
+        return fail(BLBM_ECUDA, "encoding the TMA tensor maps failed");
+    h->tma_ready = true;
+    return BLBM_OK;
+}
+
 int blbm_set_kernel(blbm_t *h, int kernel)
 {
-    if (!h) return fail(BLBM_EINVAL, "null handle");
+    CKH(h);
     switch (kernel) {
     case BLBM_KERNEL_AUTO: h->kernel = BLBM_KERNEL_VEC4; break;
     case BLBM_KERNEL_SCALAR:
     case BLBM_KERNEL_VEC4: h->kernel = kernel; break;
+    case BLBM_KERNEL_TMA: {
+        if (!h->tma_ready) {
+            int rc = tma_prepare(h);
+            if (rc) return rc;
+        }
+        h->kernel = kernel;
+        break;
+    }
     default: return fail(BLBM_EINVAL, "kernel %d not available", kernel);
     }
     return BLBM_OK;
@@ -1254,6 +1280,22 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
         if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
             return fail(BLBM_EINVAL, "block rows must be 1, 2, 4, 8 or 16");
         h->vec4_rows = value;
+        return BLBM_OK;
+    case BLBM_TUNE_TMA_TILE_ROWS:
+        if (value != 4 && value != 8) return fail(BLBM_EINVAL, "TMA tile rows must be 4 or 8");
+        if (value != h->tma_rows) {
+            h->tma_rows = value;
+            h->tma_ready = false;  // the boxes are part of the tensor maps
+            if (h->kernel == BLBM_KERNEL_TMA) return tma_prepare(h);
+        }
+        return BLBM_OK;
+    case BLBM_TUNE_TMA_STAGES:
+        if (value < 2 || value > 4) return fail(BLBM_EINVAL, "TMA stages must be 2, 3 or 4");
+        h->tma_stages = value;
+        return BLBM_OK;
+    case BLBM_TUNE_TMA_CTAS_PER_SM:
+        if (value < 1 || value > 8) return fail(BLBM_EINVAL, "TMA CTAs per SM must be 1..8");
+        h->tma_ctas = value;
         return BLBM_OK;
     default: return fail(BLBM_EINVAL, "unknown tuning knob %d", knob);
     }

@@ -1,0 +1,120 @@
+// step_common.cuh — pieces shared by the four-cells-per-thread step kernels (register/shuffle gather in
+// kernels.cu, TMA-staged gather in tma_kernel.cu): everything after the gather of one group of four
+// consecutive cells — own-copy reload of skipped cells, the flat-index wrap at column W-1, collision,
+// stores, moments, halo mirroring.
+#pragma once
+#include "blbm_internal.cuh"
+
+namespace blbmk {
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void stg4(float *p, const float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// Offset of the cell population d is pulled from, for the cell at (x, device-row offset `i`).
+// Column W-1 follows the reference's flat indexing: i+1 is (0, y+1)  (SURVEY.md section 8 a-4).
+__device__ __forceinline__ size_t pull_src(const size_t i, const uint32_t x, const int d, const uint32_t W,
+                                           const uint32_t P)
+{
+    const int dx = dir_dx(d), dy = dir_dy(d);
+    if (dx < 0 && x == W - 1) {
+        // source = flat index i + 1 - dy*W  ->  column 0 of row (y + 1 - dy)
+        return i - x + (size_t)((1 - dy)) * P;
+    }
+    return (size_t)((ptrdiff_t)i - dx - (ptrdiff_t)dy * (ptrdiff_t)P);
+}
+
+// does a cell with class word c continue from its own copy in the destination buffer?
+__device__ __forceinline__ bool reloads_own(const uint32_t c)
+{
+    return (c & (CLS_SKIP | CLS_CHAIN)) == CLS_SKIP;
+}
+
+// g[q][d]: gathered (pulled, bounce-back already applied) populations of cells x4+q, q = 0..3, at plane
+// offset i; c0..c3 their class words; vr their rest populations.
+template <bool MOM>
+__device__ __forceinline__ void finish_group(const StepParams &p, const size_t i, const uint32_t x4, const uint32_t r,
+                                             float (&g)[4][8], const uint32_t c0, const uint32_t c1,
+                                             const uint32_t c2, const uint32_t c3, const float4 vr)
+{
+    const uint32_t P = p.P, W = p.W;
+    const uint32_t cany = c0 | c1 | c2 | c3;
+    const bool ragged = x4 + 4 > W - 1;  // group holds column W-1 or cells beyond the row end
+    if ((cany & CLS_SKIP) || ragged) {
+        const bool o0 = reloads_own(c0), o1 = reloads_own(c1), o2 = reloads_own(c2), o3 = reloads_own(c3);
+        if (o0 | o1 | o2 | o3) {
+            // skipped cells continue from their own stale copy in the destination buffer
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                const float4 o = ldg4(p.Y[d] + i);
+                if (o0) g[0][d] = o.x;
+                if (o1) g[1][d] = o.y;
+                if (o2) g[2][d] = o.z;
+                if (o3) g[3][d] = o.w;
+            }
+        }
+        if (ragged) {
+            const uint32_t j = W - 1 - x4;  // position of column W-1 inside the group (0..3), if present
+            if (j < 4) {
+                const uint32_t cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
+                if (!(cj & CLS_SKIP)) {
+                    const size_t ij = i + j;
+#pragma unroll
+                    for (int d = 0; d < 8; d++) {
+                        if (dir_dx(d) < 0 && !(cj & cls_upstream_bit(d))) {
+                            const float v = p.X[d][pull_src(ij, W - 1, d, W, P)];
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if (q == (int)j) g[q][d] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    float rr[4] = {vr.x, vr.y, vr.z, vr.w};
+    float mx[4], my[4], rho[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], p.omega, mx[q], my[q], rho[q]);
+
+    // cells beyond the row end (ragged W) are padding: written, never read
+    stg4(p.R + i, make_float4(rr[0], rr[1], rr[2], rr[3]));
+#pragma unroll
+    for (int d = 0; d < 8; d++) stg4(p.Y[d] + i, make_float4(g[0][d], g[1][d], g[2][d], g[3][d]));
+    if (MOM) {
+        if (cany & CLS_CHAIN) {
+            // keep the moments the barrier-chain kernel stored at chain cells
+            const float4 ex = ldg4(p.mx + i), ey = ldg4(p.my + i), er = ldg4(p.rho + i);
+            if (c0 & CLS_CHAIN) { mx[0] = ex.x; my[0] = ey.x; rho[0] = er.x; }
+            if (c1 & CLS_CHAIN) { mx[1] = ex.y; my[1] = ey.y; rho[1] = er.y; }
+            if (c2 & CLS_CHAIN) { mx[2] = ex.z; my[2] = ey.z; rho[2] = er.z; }
+            if (c3 & CLS_CHAIN) { mx[3] = ex.w; my[3] = ey.w; rho[3] = er.w; }
+        }
+        stg4(p.mx + i, make_float4(mx[0], mx[1], mx[2], mx[3]));
+        stg4(p.my + i, make_float4(my[0], my[1], my[2], my[3]));
+        stg4(p.rho + i, make_float4(rho[0], rho[1], rho[2], rho[3]));
+    }
+    // mirror the cells a neighbouring slab gathers from into its halo rows (NVLink stores)
+    if (r == 0 && p.push.up_n) {
+        stg4(p.push.up_n + x4, make_float4(g[0][D_N], g[1][D_N], g[2][D_N], g[3][D_N]));
+        stg4(p.push.up_ne + x4, make_float4(g[0][D_NE], g[1][D_NE], g[2][D_NE], g[3][D_NE]));
+        stg4(p.push.up_nw + x4, make_float4(g[0][D_NW], g[1][D_NW], g[2][D_NW], g[3][D_NW]));
+        if (x4 == 0) p.push.up_w[0] = g[0][D_W];
+        if (MOM) {
+            stg4(p.push.up_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stg4(p.push.up_my + x4, make_float4(my[0], my[1], my[2], my[3]));
+        }
+    }
+    if (r == 1 && x4 == 0 && p.push.up_nw2) p.push.up_nw2[0] = g[0][D_NW];
+    if (r == p.rows - 1 && p.push.dn_s) {
+        stg4(p.push.dn_s + x4, make_float4(g[0][D_S], g[1][D_S], g[2][D_S], g[3][D_S]));
+        stg4(p.push.dn_se + x4, make_float4(g[0][D_SE], g[1][D_SE], g[2][D_SE], g[3][D_SE]));
+        stg4(p.push.dn_sw + x4, make_float4(g[0][D_SW], g[1][D_SW], g[2][D_SW], g[3][D_SW]));
+        if (MOM) {
+            stg4(p.push.dn_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stg4(p.push.dn_my + x4, make_float4(my[0], my[1], my[2], my[3]));
+        }
+    }
+}
+
+}  // namespace blbmk

@@ -14,7 +14,7 @@ from tests.util import (assert_same_bits, compare_state, disc_pairs, porous_pair
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [Kernel.Scalar, Kernel.Vec4]
+KERNELS = [Kernel.Scalar, Kernel.Vec4, Kernel.Tma]
 # barrier cells kept densely in the planes (0) or in the compact chain table, forced on (1)
 LAZY = [0, 1]
 
@@ -209,5 +209,6 @@ def test_full_size_properties_4096():
         assert_same_bits(lbm.read_population(5)[:, 0], inlet0, "inlet column e")
         res[kernel] = [lbm.read_population(k) for k in (0, 4, 5, 8)] + list(lbm.read_moments())
         lbm.close()
-    for a, b in zip(res[KERNELS[0]], res[KERNELS[1]]):
-        assert_same_bits(a, b, "scalar vs vec4 at 4096^2")
+    for other in KERNELS[1:]:
+        for a, b in zip(res[KERNELS[0]], res[other]):
+            assert_same_bits(a, b, f"scalar vs {other.name} at 4096^2")
