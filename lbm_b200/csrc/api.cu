@@ -109,6 +109,7 @@ struct blbm {
     int stat = BLBM_CURL;
     uint64_t step = 0, frame = 0;
     int kernel = BLBM_KERNEL_VEC4;
+    int vec4_dense = -1;  // bounce-back flavour of the vec4 kernel: -1 auto, 0 sparse, 1 dense
     int vec4_rows = 4;  // rows per block of the vec4 kernel (tuning knob; 4 measured best on the porous case)
     // TMA-staged kernel: tensor maps (opaque 128-byte descriptors) and launch shape
     alignas(64) unsigned char tma_maps[16 * 128];
@@ -314,7 +315,11 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
         e = launch_step_tma(p, mode, mom, h->tma_maps, h->tma_map_rest, xbuf, h->tma_rows, h->tma_stages, h->tma_ctas,
                             h->stream);
         break;
-    default: e = launch_step_vec4(p, mode, mom, h->vec4_rows, h->stream); break;
+    default:
+        // the obstacle-dense flavour wherever the chain table is in use (>= 2 % barrier cells), unless overridden
+        e = launch_step_vec4(p, mode, mom, h->vec4_rows, h->vec4_dense < 0 ? h->chain_active : h->vec4_dense != 0,
+                             h->stream);
+        break;
     }
     if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
@@ -1280,6 +1285,10 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
         if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
             return fail(BLBM_EINVAL, "block rows must be 1, 2, 4, 8 or 16");
         h->vec4_rows = value;
+        return BLBM_OK;
+    case BLBM_TUNE_VEC4_DENSE:
+        if (value < -1 || value > 1) return fail(BLBM_EINVAL, "dense flavour must be -1 (auto), 0 or 1");
+        h->vec4_dense = value;
         return BLBM_OK;
     case BLBM_TUNE_TMA_TILE_ROWS:
         if (value != 4 && value != 8) return fail(BLBM_EINVAL, "TMA tile rows must be 4 or 8");

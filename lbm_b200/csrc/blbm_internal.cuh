@@ -146,7 +146,8 @@ enum StepMode { MODE_FUSED = 0, MODE_COLLIDE_ONLY = 1, MODE_STREAM_ONLY = 2 };
 
 // launchers (kernels.cu)
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
-cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, cudaStream_t st);
+cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, bool dense_obstacles,
+                             cudaStream_t st);
 
 // TMA-staged variant (tma_kernel.cu).  The tensor maps are opaque 128-byte blobs owned by the handle:
 // 16 population maps (buffer-major, Dir order) and one for the rest plane, encoded for `tile_rows`.
