@@ -204,7 +204,8 @@ typedef enum blbm_tune {
     BLBM_TUNE_TMA_TILE_ROWS = 1,   /* rows per TMA tile: 4 (default) or 8 */
     BLBM_TUNE_TMA_STAGES = 2,      /* depth of the shared-memory ring: 2..4 (default 4) */
     BLBM_TUNE_TMA_CTAS_PER_SM = 3, /* persistent CTAs per SM: 1..8 (default 2) */
-    BLBM_TUNE_VEC4_DENSE = 4       /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles */
+    BLBM_TUNE_VEC4_DENSE = 4,      /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles */
+    BLBM_TUNE_CUDA_GRAPHS = 5      /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
 } blbm_tune;
 int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale

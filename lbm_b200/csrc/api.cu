@@ -131,6 +131,13 @@ struct blbm {
     size_t chain_n = 0, chain_cap = 0;
     unsigned long long *chain_counter = nullptr;
     unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
+    // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): GRAPH_CHUNK fused steps are
+    // captured once into a CUDA graph per start parity and replayed.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long sig[4] = {0, 0, 0, 0};
+    } graph[2];
+    int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
 };
 
 namespace {
@@ -357,10 +364,68 @@ int run_summary(blbm *h)
     return BLBM_OK;
 }
 
+constexpr uint32_t GRAPH_CHUNK = 8;  // even, so a replay starts on the parity it was captured for
+
+bool graphs_wanted(const blbm *h)
+{
+    if (any_peer(h) || h->kernel == BLBM_KERNEL_TMA) return false;  // peers: per-step handshake kernels
+    if (h->use_graphs >= 0) return h->use_graphs != 0;
+    return (unsigned long long)h->rows * h->W <= (4ull << 20);
+}
+
+// GRAPH_CHUNK fused, non-moment-storing steps starting at the current parity, as one graph launch
+int run_step_graph(blbm *h)
+{
+    const int par = (int)(h->step % 2);
+    blbm::StepGraph &g = h->graph[par];
+    unsigned int omega_bits;
+    memcpy(&omega_bits, &h->omega, sizeof(omega_bits));
+    const unsigned long long sig[4] = {
+        1ull + (unsigned long long)h->cls_cur, omega_bits,
+        (unsigned long long)h->kernel | ((unsigned long long)h->vec4_rows << 8) |
+            ((unsigned long long)(h->vec4_dense + 1) << 16) | ((unsigned long long)h->chain_active << 24),
+        (unsigned long long)(uintptr_t)h->pool};
+    if (!g.exec || memcmp(g.sig, sig, sizeof(sig)) != 0) {
+        if (g.exec) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = BLBM_OK;
+        const uint64_t step0 = h->step;
+        for (uint32_t q = 0; q < GRAPH_CHUNK && rc == BLBM_OK; q++) {
+            const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
+            rc = launch_step(h, MODE_FUSED, x, y, false);
+            h->step++;
+        }
+        h->step = step0;
+        h->launches -= GRAPH_CHUNK;  // capture enqueues nothing
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != BLBM_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            g.exec = nullptr;
+            return fail(BLBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        }
+        memcpy(g.sig, sig, sizeof(sig));
+    }
+    CK(cudaGraphLaunch(g.exec, h->stream));
+    h->step += GRAPH_CHUNK;
+    h->launches += GRAPH_CHUNK;
+    return BLBM_OK;
+}
+
 int do_steps(blbm *h, uint32_t n)
 {
     uint32_t left = n;
     bool replayed = false;
+    const bool graphs = graphs_wanted(h);
     while (left) {
         const bool mom = left == 1;
         int rc;
@@ -372,6 +437,11 @@ int do_steps(blbm *h, uint32_t n)
                                    (uint32_t)(h->step % 2), h->omega, h->mx, h->my, h->rho, h->stream));
             h->launches++;
             replayed = true;
+        }
+        if (graphs && h->regimeT && !h->cls_pending && left > GRAPH_CHUNK) {
+            if ((rc = run_step_graph(h)) != BLBM_OK) return rc;
+            left -= GRAPH_CHUNK;
+            continue;
         }
         if (!h->regimeT) {
             // collide of step `step`, in place on the live buffer (collision/*.wgsl); its stream stays pending
@@ -770,6 +840,8 @@ int blbm_destroy(blbm_t *h)
         stream_free(h->chain_state, h->stream);
         cudaStreamSynchronize(h->stream);
     }
+    for (int q = 0; q < 2; q++)
+        if (h->graph[q].exec) cudaGraphExecDestroy(h->graph[q].exec);
     if (h->mailbox_host) cudaFreeHost(h->mailbox_host);
     if (h->pool) cudaFree(h->pool);
     if (h->copy_stream) {
@@ -1289,6 +1361,10 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
     case BLBM_TUNE_VEC4_DENSE:
         if (value < -1 || value > 1) return fail(BLBM_EINVAL, "dense flavour must be -1 (auto), 0 or 1");
         h->vec4_dense = value;
+        return BLBM_OK;
+    case BLBM_TUNE_CUDA_GRAPHS:
+        if (value < -1 || value > 1) return fail(BLBM_EINVAL, "graphs must be -1 (auto), 0 or 1");
+        h->use_graphs = value;
         return BLBM_OK;
     case BLBM_TUNE_TMA_TILE_ROWS:
         if (value != 4 && value != 8) return fail(BLBM_EINVAL, "TMA tile rows must be 4 or 8");
