@@ -64,6 +64,7 @@ extern "C" {
     pub fn blbm_exchange_halos(h: *mut blbm_t) -> c_int;
     pub fn blbm_set_kernel(h: *mut blbm_t, kernel: c_int) -> c_int;
     pub fn blbm_get_kernel(h: *const blbm_t) -> c_int;
+    pub fn blbm_set_tuning(h: *mut blbm_t, knob: c_int, value: c_int) -> c_int;
     pub fn blbm_set_lazy_barriers(h: *mut blbm_t, mode: c_int) -> c_int;
     pub fn blbm_get_lazy_barriers_active(h: *const blbm_t) -> c_int;
     pub fn blbm_get_launch_count(h: *const blbm_t) -> u64;
