@@ -12,6 +12,7 @@ Workloads (BASELINE.json configs):
     channel16384 the same lattice without the porous mask (isolates the cost of the mask)
     cavity4096   configs[1]: 4096 x 4096 closed box
     cylinder512  configs[0]: 512 x 256 channel past a cylinder (L2-resident, launch-bound; not a roofline case)
+    cylinder32768 configs[3]: 32768^2 cylinder wake, strong scaling (the lattice is fixed, N slabs)
     channel65536 configs[4]: 65536 x 8192 per GPU (65536^2 on 8 GPUs), one cylinder
 At N > 1 the lattice is N slabs stacked in y (weak scaling: per-GPU work fixed), linked by direct NVLink
 halo stores from the step kernel; no NCCL collective is on the data path.
@@ -39,7 +40,11 @@ WORKLOADS = {
     "cavity4096": (4096, 4096, 1.25, 0.1, "box"),
     "cylinder512": (512, 256, 1.0 / (3 * 0.02 + 0.5), 0.1, "cylinder"),
     "channel65536": (65536, 8192, 1.0, 0.05, "cylinder"),
+    # configs[3]: 32768 x 32768 cylinder wake, Re 1000 (nu = 0.0512); STRONG scaling: the lattice is fixed and
+    # split into N slabs (rows/GPU below is the N = 1 value)
+    "cylinder32768": (32768, 32768, 1.0 / (3 * 0.0512 + 0.5), 0.1, "cylinder"),
 }
+STRONG = {"cylinder32768"}
 
 
 def splitmix64(x):
@@ -235,7 +240,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     w, rows_gpu, omega, u0, kind = WORKLOADS[args.workload]
-    h_total = rows_gpu * world
+    strong = args.workload in STRONG
+    if strong:
+        h_total = rows_gpu
+        rows_gpu = h_total // world
+    else:
+        h_total = rows_gpu * world
     r0, r1 = rank * rows_gpu, (rank + 1) * rows_gpu
     kernel = {"auto": Kernel.Auto, "scalar": Kernel.Scalar, "vec4": Kernel.Vec4, "tma": Kernel.Tma}[args.kernel]
     lbm = LBM(omega, w, h_total, inflow_ux=u0, device=local, rows=(r0, r1), kernel=kernel,
@@ -351,7 +361,8 @@ def main():
 
     line = {
         "metric": "MLUPS (D2Q9 fp32)", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "W": w, "H": h_total, "H_per_gpu": rows_gpu, "omega": omega, "u0": u0,
                    "mask": kind, "kernel": lbm.get_kernel().name.lower(), "parallelism": f"y-slabs x{world}",

@@ -145,6 +145,22 @@ int blbm_reset_barrier(blbm_t *h);
  * slab may be handed the same data or just its own window. */
 int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const uint8_t *mask);
 
+/* ---- barrier shapes: the host-side rasteriser in front of draw_points (barrier_shapes/line.rs) ------------ */
+
+/* Line::new (erase = 0, line.rs:22-54) / Line::new_erased (erase != 0, line.rs:56-87, 30 wide) without a handle:
+ * the distinct cells of the thick line between two end points on an xdim x ydim lattice, as (x, y) pairs in
+ * xy[0 .. 2*min(count, capacity)), ordered by (x, y).  BLBM_EINVAL when an end point lies outside the lattice
+ * (the reference returns Err there).  Pure host code: works without a GPU. */
+int blbm_rasterize_line(int64_t x1, int64_t y1, int64_t x2, int64_t y2, int64_t xdim, int64_t ydim, int erase,
+                        int64_t *xy, size_t capacity, size_t *count);
+/* draw_shape(&Line::new(..)) / draw_shape(&Line::new_erased(..)) */
+int blbm_draw_line(blbm_t *h, int64_t x1, int64_t y1, int64_t x2, int64_t y2);
+int blbm_erase_line(blbm_t *h, int64_t x1, int64_t y1, int64_t x2, int64_t y2);
+/* LBM::curl_barrier / chaos_barrier / welcome_barrier, lbm.rs:1367-1480 (callers reset_barrier first, lib.rs:120-128) */
+int blbm_curl_barrier(blbm_t *h);
+int blbm_chaos_barrier(blbm_t *h);
+int blbm_welcome_barrier(blbm_t *h);
+
 /* ---- counters, lbm.rs:1166-1172 ---------------------------------------------------------------- */
 uint64_t blbm_get_compute_num(const blbm_t *h);
 uint64_t blbm_get_frame_num(const blbm_t *h);
@@ -168,6 +184,14 @@ int blbm_read_barrier(blbm_t *h, uint32_t *dst);
 /* per-cell classification: bit0 barrier, bit1 skipped by stream (barrier | x==0 | y>=H-1), bits 2..9
  * "upstream neighbour is a barrier" for nw n ne w e sw s se */
 int blbm_read_cell_class(blbm_t *h, uint16_t *dst);
+
+/* ColorMap, lbm.rs:18-24 (same order) */
+typedef enum blbm_colormap { BLBM_INFERNO = 0, BLBM_VIRIDIS = 1, BLBM_JET = 2 } blbm_colormap;
+/* LBM::color_map, lbm.rs:1299-1335 (color_map/{inferno,viridis,jet}.wgsl): piece-wise linear LUT of the output
+ * field into RGB, barrier cells black.  The colours stay on the device (rows x W x 3 fp32, densely packed — the
+ * reference's array<vec3<f32>> has a 16-byte stride in a buffer sized for 12, lbm.rs:193; not reproduced). */
+int blbm_color_map(blbm_t *h, int map);
+int blbm_read_colors(blbm_t *h, float *rgb);
 
 /* Asynchronous variants for frame pipelines: dst must be page-locked (cudaHostAlloc / pinned torch
  * tensor); the copy is ordered after everything enqueued so far and overlaps later work.  Complete

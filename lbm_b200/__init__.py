@@ -5,8 +5,8 @@ host-side mirror of the reference's `pub struct LBM` (lbm-wgpu/src/lbm.rs:32-98)
 ctypes, used by the tests, the bench and Python callers.  There is no CPU path: importing works
 anywhere, but constructing an `LBM` without the built library or without a GPU raises.
 """
-from .lbm import (LBM, SlabGroup, BlbmError, SummaryStat, Kernel, POP_NAMES, library_path, load_library,
-                  omega_from_viscosity)
+from .lbm import (LBM, SlabGroup, BlbmError, SummaryStat, ColorMap, Kernel, POP_NAMES, library_path, load_library,
+                  omega_from_viscosity, rasterize_line)
 
-__all__ = ["LBM", "SlabGroup", "BlbmError", "SummaryStat", "Kernel", "POP_NAMES", "library_path",
-           "load_library", "omega_from_viscosity"]
+__all__ = ["LBM", "SlabGroup", "BlbmError", "SummaryStat", "ColorMap", "Kernel", "POP_NAMES", "library_path",
+           "load_library", "omega_from_viscosity", "rasterize_line"]

@@ -138,6 +138,7 @@ struct blbm {
         unsigned long long sig[4] = {0, 0, 0, 0};
     } graph[2];
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
+    float *rgb = nullptr;  // colour buffer (rows x W x 3), allocated by the first blbm_color_map
 };
 
 namespace {
@@ -835,6 +836,7 @@ int blbm_destroy(blbm_t *h)
     if (h->up.ipc_opened) cudaIpcCloseMemHandle(h->up.base);
     if (h->dn.ipc_opened) cudaIpcCloseMemHandle(h->dn.base);
     if (h->stream) {
+        stream_free(h->rgb, h->stream);
         stream_free(h->d_pairs, h->stream);
         stream_free(h->chain_idx, h->stream);
         stream_free(h->chain_state, h->stream);
@@ -1155,6 +1157,32 @@ int blbm_read_output(blbm_t *h, float *dst)
     if (!dst) return fail(BLBM_EINVAL, "dst is null");
     int rc = copy_plane_to_host(h, h->out, dst);
     if (rc) return rc;
+    return sync_stream(h);
+}
+
+int blbm_color_map(blbm_t *h, int map)
+{
+    CKH(h);
+    if (map < 0 || map > 2) return fail(BLBM_EINVAL, "colour map %d out of range", map);
+    if (!h->rgb) {
+        const size_t bytes = (size_t)h->rows * h->W * 3 * sizeof(float);
+        if (stream_alloc((void **)&h->rgb, bytes, h->stream) != cudaSuccess) {
+            cudaGetLastError();
+            h->rgb = nullptr;
+            return fail(BLBM_ENOMEM, "allocating %zu bytes for the colour buffer failed", bytes);
+        }
+    }
+    CK(launch_color_map(h->out, h->mask, h->rgb, geom(h), map, h->stream));
+    h->launches++;
+    return BLBM_OK;
+}
+
+int blbm_read_colors(blbm_t *h, float *rgb)
+{
+    CKH(h);
+    if (!rgb) return fail(BLBM_EINVAL, "rgb is null");
+    if (!h->rgb) return fail(BLBM_ESTATE, "blbm_color_map has not been called");
+    CK(cudaMemcpyAsync(rgb, h->rgb, (size_t)h->rows * h->W * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     return sync_stream(h);
 }
 

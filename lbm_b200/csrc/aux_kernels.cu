@@ -645,3 +645,68 @@ cudaError_t launch_chain_replay(const uint32_t *idx, float *state, size_t n, siz
 }
 
 }  // namespace blbmk
+
+// ================================================================================================
+// Colour maps: rewritten_shaders/color_map/{jet,viridis,inferno}.wgsl.
+// Piece-wise linear LUT of the output field, barrier cells black.  rgb is rows x W x 3 floats, dense.
+// ================================================================================================
+namespace blbmk {
+
+__constant__ float c_cmap_nodes[3][9][3] = {
+    // Inferno = 0
+    {{0.98828125f, 1.0f, 0.64453125f}, {0.97265625f, 0.55859375f, 0.0390625f}, {0.73828125f, 0.21875f, 0.33203125f},
+     {0.34375f, 0.06640625f, 0.43359375f}, {0.0f, 0.0f, 0.01853125f}},
+    // Viridis = 1
+    {{0.9921875f, 0.90625f, 0.1484375f}, {0.3671875f, 0.7890625f, 0.3828125f}, {0.1328125f, 0.56640625f, 0.55078125f},
+     {0.23046875f, 0.32421875f, 0.546875f}, {0.265625f, 0.0078125f, 0.33203125f}},
+    // Jet = 2
+    {{0.0f, 0.0f, 0.5f}, {0.0f, 0.0f, 1.0f}, {0.0f, 0.5f, 1.0f}, {0.0f, 1.0f, 1.0f}, {0.5f, 1.0f, 0.5f},
+     {1.0f, 1.0f, 0.0f}, {1.0f, 0.5f, 0.0f}, {1.0f, 0.0f, 0.0f}, {0.5f, 0.0f, 0.0f}}};
+
+__global__ void color_map_kernel(const float *__restrict__ out, const uint8_t *__restrict__ mask, float *__restrict__ rgb,
+                                 const SlabGeom g, const int map)
+{
+    const int nseg = map == 2 ? 8 : 4;
+    const float scale = map == 2 ? 20.0f : 15.0f;
+    const float lo = (float)(-nseg / 2), hi = (float)(nseg / 2);
+    const int ilo = -nseg / 2;
+    const size_t total = (size_t)g.rows * g.W;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / g.W);
+        const uint32_t x = (uint32_t)(t - (size_t)r * g.W);
+        float c = __fmul_rn(scale, out[row_off(r, g.P) + x]);
+        c = fminf(fmaxf(c, lo), hi);
+        const int block = (int)floorf(c);
+        float cr, cg, cb;
+        if (block >= ilo && block < ilo + nseg) {
+            const float rw = __fadd_rn((float)(-block), c);
+            const float lw = __fsub_rn(1.0f, rw);
+            const float *A = c_cmap_nodes[map][block - ilo], *B = c_cmap_nodes[map][block - ilo + 1];
+            cr = __fadd_rn(__fmul_rn(lw, A[0]), __fmul_rn(rw, B[0]));
+            cg = __fadd_rn(__fmul_rn(lw, A[1]), __fmul_rn(rw, B[1]));
+            cb = __fadd_rn(__fmul_rn(lw, A[2]), __fmul_rn(rw, B[2]));
+        } else {
+            cr = c_cmap_nodes[map][nseg][0];
+            cg = c_cmap_nodes[map][nseg][1];
+            cb = c_cmap_nodes[map][nseg][2];
+        }
+        if (mask[mask_row_off(r, g.P) + x] == 1) cr = cg = cb = 0.0f;
+        rgb[3 * t + 0] = cr;
+        rgb[3 * t + 1] = cg;
+        rgb[3 * t + 2] = cb;
+    }
+}
+
+cudaError_t launch_color_map(const float *out, const uint8_t *mask, float *rgb, const SlabGeom &g, int map,
+                             cudaStream_t st)
+{
+    const size_t total = (size_t)g.rows * g.W;
+    size_t nb = (total + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    if (nb == 0) return cudaSuccess;
+    color_map_kernel<<<(unsigned)nb, 256, 0, st>>>(out, mask, rgb, g, map);
+    return cudaGetLastError();
+}
+
+}  // namespace blbmk

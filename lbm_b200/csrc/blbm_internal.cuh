@@ -184,6 +184,8 @@ cudaError_t launch_precollision_moments(const float *const *f8, float *mx, float
                                         cudaStream_t st);
 cudaError_t launch_summary(int stat, const float *mx, const float *my, const float *rho, float *out,
                            const SlabGeom &g, cudaStream_t st);
+cudaError_t launch_color_map(const float *out, const uint8_t *mask, float *rgb, const SlabGeom &g, int map,
+                             cudaStream_t st);
 cudaError_t launch_reduce(const float *mx, const float *my, const float *rho, const float *out,
                           const SlabGeom &g, double *sums3, float *maxabs, cudaStream_t st);
 // barrier chains (see aux_kernels.cu)

@@ -39,6 +39,12 @@ class SummaryStat(enum.IntEnum):  # lbm.rs:10-16
     Speed = 4
 
 
+class ColorMap(enum.IntEnum):  # lbm.rs:18-24
+    Inferno = 0
+    Viridis = 1
+    Jet = 2
+
+
 class Kernel(enum.IntEnum):
     Auto = 0
     Scalar = 1
@@ -92,6 +98,13 @@ PROTOTYPES = {
     "blbm_write_barrier_rows": (_I, [_P, _U64, _U64, _P]),
     "blbm_timer_start": (_I, [_P]),
     "blbm_timer_stop": (_I, [_P, C.POINTER(_F)]),
+    "blbm_rasterize_line": (_I, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _I, _P, _SZ,
+                                 C.POINTER(_SZ)]),
+    "blbm_draw_line": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "blbm_erase_line": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "blbm_curl_barrier": (_I, [_P]),
+    "blbm_chaos_barrier": (_I, [_P]),
+    "blbm_welcome_barrier": (_I, [_P]),
     "blbm_get_compute_num": (_U64, [_P]),
     "blbm_get_frame_num": (_U64, [_P]),
     "blbm_read_population": (_I, [_P, _I, _I, _P]),
@@ -100,6 +113,8 @@ PROTOTYPES = {
     "blbm_read_output": (_I, [_P, _P]),
     "blbm_read_barrier": (_I, [_P, _P]),
     "blbm_read_cell_class": (_I, [_P, _P]),
+    "blbm_color_map": (_I, [_P, _I]),
+    "blbm_read_colors": (_I, [_P, _P]),
     "blbm_read_output_async": (_I, [_P, _P]),
     "blbm_synchronize": (_I, [_P]),
     "blbm_reduce_moments": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -249,6 +264,22 @@ class LBM:
     def reset_barrier(self):
         _check(self._L.blbm_reset_barrier(self._h))
 
+    def draw_line(self, p1, p2):
+        """draw_shape(&Line::new(p1, p2, x, y)) — the thick Bresenham line of barrier_shapes/line.rs"""
+        _check(self._L.blbm_draw_line(self._h, int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1])))
+
+    def erase_line(self, p1, p2):
+        _check(self._L.blbm_erase_line(self._h, int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1])))
+
+    def curl_barrier(self):
+        _check(self._L.blbm_curl_barrier(self._h))
+
+    def chaos_barrier(self):
+        _check(self._L.blbm_chaos_barrier(self._h))
+
+    def welcome_barrier(self):
+        _check(self._L.blbm_welcome_barrier(self._h))
+
     def write_barrier_rows(self, row_begin, mask_rows):
         """mask_rows: (nrows, W) uint8, 1 = barrier, for global rows [row_begin, row_begin+nrows)."""
         a = np.ascontiguousarray(mask_rows, dtype=np.uint8)
@@ -291,6 +322,15 @@ class LBM:
     def read_output(self):
         out = np.empty(self._shape(), np.float32)
         _check(self._L.blbm_read_output(self._h, out.ctypes.data))
+        return out
+
+    def color_map(self, cmap):
+        """LBM::color_map (lbm.rs:1299): LUT of the output field into RGB on the device."""
+        _check(self._L.blbm_color_map(self._h, int(cmap)))
+
+    def read_colors(self):
+        out = np.empty(self._shape() + (3,), np.float32)
+        _check(self._L.blbm_read_colors(self._h, out.ctypes.data))
         return out
 
     def read_output_async(self, pinned_ptr):
@@ -349,6 +389,20 @@ class LBM:
 
     def device_bytes(self):
         return int(self._L.blbm_get_device_bytes(self._h))
+
+
+def rasterize_line(p1, p2, xdim, ydim, erase=False):
+    """Cells of Line::new / Line::new_erased as an (n, 2) int64 array of (x, y); None for invalid end points."""
+    L = load_library()
+    n = _SZ()
+    rc = L.blbm_rasterize_line(int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]), int(xdim), int(ydim), int(erase), None,
+                               0, C.byref(n))
+    if rc != 0:
+        return None
+    out = np.empty((n.value, 2), np.int64)
+    L.blbm_rasterize_line(int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]), int(xdim), int(ydim), int(erase),
+                          out.ctypes.data, n.value, C.byref(n))
+    return out
 
 
 def slab_rows(y, nslabs):

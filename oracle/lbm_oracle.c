@@ -438,3 +438,57 @@ int lbm_oracle_threads(void)
     return 1;
 #endif
 }
+
+/* ---- colour maps (row N3 of SURVEY.md section 8f): rewritten_shaders/color_map/{jet,viridis,inferno}.wgsl
+ * through lbm.rs:1299-1335.  rgb is n x 3 floats, densely packed (the reference's array<vec3<f32>> has a
+ * 16-byte stride in a buffer sized for 12, lbm.rs:193 vs jet.wgsl:1 — a latent bug that is not restated).
+ * ColorMap order, lbm.rs:18-24: Inferno = 0, Viridis = 1, Jet = 2. ---- */
+static const float JET_NODES[9][3] = {{0.0f, 0.0f, 0.5f}, {0.0f, 0.0f, 1.0f}, {0.0f, 0.5f, 1.0f},
+                                      {0.0f, 1.0f, 1.0f}, {0.5f, 1.0f, 0.5f}, {1.0f, 1.0f, 0.0f},
+                                      {1.0f, 0.5f, 0.0f}, {1.0f, 0.0f, 0.0f}, {0.5f, 0.0f, 0.0f}};
+static const float VIRIDIS_NODES[5][3] = {{0.9921875f, 0.90625f, 0.1484375f},
+                                          {0.3671875f, 0.7890625f, 0.3828125f},
+                                          {0.1328125f, 0.56640625f, 0.55078125f},
+                                          {0.23046875f, 0.32421875f, 0.546875f},
+                                          {0.265625f, 0.0078125f, 0.33203125f}};
+static const float INFERNO_NODES[5][3] = {{0.98828125f, 1.0f, 0.64453125f},
+                                          {0.97265625f, 0.55859375f, 0.0390625f},
+                                          {0.73828125f, 0.21875f, 0.33203125f},
+                                          {0.34375f, 0.06640625f, 0.43359375f},
+                                          {0.0f, 0.0f, 0.01853125f}};
+
+void lbm_oracle_color_map(const lbm_oracle *o, int map, float *rgb)
+{
+    const float(*nodes)[3];
+    int nseg;
+    float scale;
+    if (map == 2) {
+        nodes = JET_NODES; nseg = 8; scale = 20.0f;      /* jet.wgsl:16: clamp(20 v, -4, 4) */
+    } else if (map == 1) {
+        nodes = VIRIDIS_NODES; nseg = 4; scale = 15.0f;  /* viridis.wgsl:16: clamp(15 v, -2, 2) */
+    } else {
+        nodes = INFERNO_NODES; nseg = 4; scale = 15.0f;
+    }
+    const float lo = (float)(-nseg / 2), hi = (float)(nseg / 2);
+    const int ilo = -nseg / 2;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < o->n; i++) {
+        float c = scale * o->out[i];
+        c = c > lo ? c : lo; /* clamp = min(max(e, low), high) */
+        c = c < hi ? c : hi;
+        const int block = (int)floorf(c);
+        float r, g, b;
+        if (block >= ilo && block < ilo + nseg) {
+            const float rw = (float)(-block) + c; /* "4.0 + color", "3.0 + color", ... "-3.0 + color" */
+            const float lw = 1.0f - rw;
+            const float *A = nodes[block - ilo], *B = nodes[block - ilo + 1];
+            r = lw * A[0] + rw * B[0];
+            g = lw * A[1] + rw * B[1];
+            b = lw * A[2] + rw * B[2];
+        } else { /* default: the last node */
+            r = nodes[nseg][0]; g = nodes[nseg][1]; b = nodes[nseg][2];
+        }
+        if (o->bar[i] == 1u) r = g = b = 0.0f;
+        rgb[3 * i + 0] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+    }
+}

@@ -50,6 +50,7 @@ def lib():
         L.lbm_oracle_single_cell.argtypes = [P, C.c_uint32]
         L.lbm_oracle_cell_class.argtypes = [P, P]
         L.lbm_oracle_set_equil.argtypes = [C.c_float, C.c_float, C.c_float, P]
+        L.lbm_oracle_color_map.argtypes = [P, C.c_int, P]
         L.lbm_oracle_population.restype = P
         L.lbm_oracle_population.argtypes = [P, C.c_int, C.c_int]
         for name in ("barrier", "mx", "my", "rho", "output"):
@@ -154,6 +155,12 @@ class Oracle:
 
     def output(self):
         return self._view(self._L.lbm_oracle_output(self._h), np.float32)
+
+    def color_map(self, cmap):
+        """colours of the current output field, (h, w, 3) fp32; Inferno 0, Viridis 1, Jet 2 (lbm.rs:18-24)"""
+        out = np.zeros((self.h, self.w, 3), np.float32)
+        self._L.lbm_oracle_color_map(self._h, int(cmap), out.ctypes.data)
+        return out
 
     def cell_class(self):
         out = np.zeros((self.h, self.w), np.uint16)

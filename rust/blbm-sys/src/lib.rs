@@ -44,6 +44,13 @@ extern "C" {
     pub fn blbm_draw_points64(h: *mut blbm_t, loc_val_pairs: *const u64, npairs: usize) -> c_int;
     pub fn blbm_reset_barrier(h: *mut blbm_t) -> c_int;
     pub fn blbm_write_barrier_rows(h: *mut blbm_t, row_begin: u64, nrows: u64, mask: *const u8) -> c_int;
+    pub fn blbm_rasterize_line(x1: i64, y1: i64, x2: i64, y2: i64, xdim: i64, ydim: i64, erase: c_int, xy: *mut i64,
+                               capacity: usize, count: *mut usize) -> c_int;
+    pub fn blbm_draw_line(h: *mut blbm_t, x1: i64, y1: i64, x2: i64, y2: i64) -> c_int;
+    pub fn blbm_erase_line(h: *mut blbm_t, x1: i64, y1: i64, x2: i64, y2: i64) -> c_int;
+    pub fn blbm_curl_barrier(h: *mut blbm_t) -> c_int;
+    pub fn blbm_chaos_barrier(h: *mut blbm_t) -> c_int;
+    pub fn blbm_welcome_barrier(h: *mut blbm_t) -> c_int;
     pub fn blbm_get_compute_num(h: *const blbm_t) -> u64;
     pub fn blbm_get_frame_num(h: *const blbm_t) -> u64;
     pub fn blbm_read_population(h: *mut blbm_t, buffer: c_int, k: c_int, dst: *mut c_float) -> c_int;
@@ -52,6 +59,8 @@ extern "C" {
     pub fn blbm_read_output(h: *mut blbm_t, dst: *mut c_float) -> c_int;
     pub fn blbm_read_barrier(h: *mut blbm_t, dst: *mut u32) -> c_int;
     pub fn blbm_read_cell_class(h: *mut blbm_t, dst: *mut u16) -> c_int;
+    pub fn blbm_color_map(h: *mut blbm_t, map: c_int) -> c_int;
+    pub fn blbm_read_colors(h: *mut blbm_t, rgb: *mut c_float) -> c_int;
     pub fn blbm_read_output_async(h: *mut blbm_t, pinned_dst: *mut c_float) -> c_int;
     pub fn blbm_synchronize(h: *mut blbm_t) -> c_int;
     pub fn blbm_reduce_moments(h: *mut blbm_t, sum_rho: *mut c_double, sum_mx: *mut c_double, sum_my: *mut c_double,

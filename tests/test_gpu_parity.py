@@ -212,3 +212,23 @@ def test_full_size_properties_4096():
     for other in KERNELS[1:]:
         for a, b in zip(res[KERNELS[0]], res[other]):
             assert_same_bits(a, b, f"scalar vs {other.name} at 4096^2")
+
+
+@pytest.mark.parametrize("cmap", [0, 1, 2])
+def test_color_maps_bit_exact(cmap):
+    """Row N3: color_map/{inferno,viridis,jet}.wgsl on every summary statistic."""
+    w, h = 200, 70
+    om = omega_from_viscosity(0.02)
+    lbm, ora = LBM(om, w, h), Oracle(om, w, h)
+    cyl = disc_pairs(w, 40, 35, 8)
+    lbm.draw_points(cyl)
+    ora.draw_points(cyl.astype(np.uint32))
+    lbm.iterate(300)
+    ora.iterate(300)
+    for stat in range(5):
+        lbm.compute_summary(stat)
+        ora.compute_summary(stat)
+        lbm.color_map(cmap)
+        assert_same_bits(lbm.read_colors().reshape(h, -1), ora.color_map(cmap).reshape(h, -1),
+                         f"colour map {cmap} stat {stat}")
+    lbm.close()

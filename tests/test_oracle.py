@@ -190,3 +190,49 @@ def test_state_arrays_and_digest_are_nan_canonical():
     assert digest(a) == digest(b)
     o = Oracle(1.0, 8, 4)
     assert len(state_arrays(o)) == 24
+
+
+def _numpy_color_map(out, bar, cmap):
+    """Independent vectorised restatement of color_map/{inferno,viridis,jet}.wgsl."""
+    F = np.float32
+    jet = [(0, 0, .5), (0, 0, 1), (0, .5, 1), (0, 1, 1), (.5, 1, .5), (1, 1, 0), (1, .5, 0), (1, 0, 0), (.5, 0, 0)]
+    viridis = [(0.9921875, 0.90625, 0.1484375), (0.3671875, 0.7890625, 0.3828125),
+               (0.1328125, 0.56640625, 0.55078125), (0.23046875, 0.32421875, 0.546875),
+               (0.265625, 0.0078125, 0.33203125)]
+    inferno = [(0.98828125, 1.0, 0.64453125), (0.97265625, 0.55859375, 0.0390625),
+               (0.73828125, 0.21875, 0.33203125), (0.34375, 0.06640625, 0.43359375), (0.0, 0.0, 0.01853125)]
+    nodes = np.array({0: inferno, 1: viridis, 2: jet}[cmap], F)
+    nseg = len(nodes) - 1
+    scale, lo, hi = (F(20), F(-4), F(4)) if cmap == 2 else (F(15), F(-2), F(2))
+    c = np.minimum(np.maximum(scale * out, lo), hi)
+    block = np.floor(c).astype(np.int64)
+    idx = np.clip(block + nseg // 2, 0, nseg - 1)
+    rw = (-block).astype(F) + c
+    lw = F(1) - rw
+    rgb = lw[..., None] * nodes[idx] + rw[..., None] * nodes[idx + 1]
+    rgb = np.where((block >= nseg // 2)[..., None], nodes[nseg], rgb)
+    rgb[bar == 1] = 0
+    return rgb.astype(F)
+
+
+@pytest.mark.parametrize("cmap", [0, 1, 2])
+def test_color_maps_match_numpy_and_known_colours(cmap):
+    w, h = 64, 32
+    o = Oracle(omega_from_viscosity(0.02), w, h)
+    o.draw_points(disc_pairs(w, 16, 16, 4).astype(np.uint32))
+    o.iterate(150)
+    for stat in range(5):
+        o.compute_summary(stat)
+        got = o.color_map(cmap)
+        want = _numpy_color_map(o.output(), o.barrier(), cmap)
+        assert_same_bits(got.reshape(h, -1), want.reshape(h, -1), f"colour map {cmap} stat {stat}")
+    assert (got[0] == 0).all() and (got[16, 16] == 0).all()  # walls and the disc are black (jet.wgsl:56-58)
+    # value 0 sits on the middle node; saturated values on the end nodes
+    o.output()[5, 5], o.output()[5, 6], o.output()[5, 7] = 0.0, 10.0, -10.0
+    c = o.color_map(cmap)
+    mid = {0: (0.73828125, 0.21875, 0.33203125), 1: (0.1328125, 0.56640625, 0.55078125), 2: (0.5, 1.0, 0.5)}[cmap]
+    top = {0: (0.0, 0.0, 0.01853125), 1: (0.265625, 0.0078125, 0.33203125), 2: (0.5, 0.0, 0.0)}[cmap]
+    bot = {0: (0.98828125, 1.0, 0.64453125), 1: (0.9921875, 0.90625, 0.1484375), 2: (0.0, 0.0, 0.5)}[cmap]
+    assert tuple(c[5, 5]) == tuple(np.float32(mid))
+    assert tuple(c[5, 6]) == tuple(np.float32(top))
+    assert tuple(c[5, 7]) == tuple(np.float32(bot))
