@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-typedef struct blbm blbm_t;
+typedef struct blbm_handle blbm_t;
 
 typedef enum blbm_status {
     BLBM_OK = 0,

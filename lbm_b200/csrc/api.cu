@@ -75,7 +75,7 @@ struct Peer {
 
 }  // namespace
 
-struct blbm {
+struct blbm_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -140,6 +140,7 @@ struct blbm {
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
     float *rgb = nullptr;  // colour buffer (rows x W x 3), allocated by the first blbm_color_map
 };
+typedef blbm_handle blbm;
 
 namespace {
 
