@@ -476,19 +476,26 @@ int rebuild_class(blbm *h, uint32_t lo, uint32_t hi, bool big_change)
     int target;
     uint32_t blo = lo, bhi = hi;
     if (h->regimeT) {
-        // the pending stream must still see the old classification: build the other buffer; unless a newer
-        // classification is already waiting there, that buffer is also stale wherever the two differ
+        // the pending stream must still see the old classification: build the other buffer
         target = h->cls_cur ^ 1;
         if (!h->cls_pending) {
+            // that buffer is stale wherever the two differ: refresh those rows too; afterwards it is current
+            // everywhere and the two buffers differ only where this paint changed the mask
             blo = ulo;
             bhi = uhi;
+            h->diff_lo = lo;
+            h->diff_hi = hi;
+        } else {
+            // a newer classification is already waiting there: only this paint's rows need rebuilding
+            h->diff_lo = ulo;
+            h->diff_hi = uhi;
         }
         h->cls_pending = true;
     } else {
         target = h->cls_cur;
+        h->diff_lo = ulo;
+        h->diff_hi = uhi;
     }
-    h->diff_lo = ulo;
-    h->diff_hi = uhi;
     CK(launch_build_class(h->cls[target], h->mask, geom(h), h->chain_active ? h->cls[h->cls_cur] : nullptr,
                           h->rowflag[target], blo, bhi, h->stream));
     h->launches++;
