@@ -232,3 +232,32 @@ def test_color_maps_bit_exact(cmap):
         assert_same_bits(lbm.read_colors().reshape(h, -1), ora.color_map(cmap).reshape(h, -1),
                          f"colour map {cmap} stat {stat}")
     lbm.close()
+
+
+def test_full_size_properties_16384_porous():
+    """BASELINE.json configs[2] at full size (16384^2, 15 % porous mask — far beyond what the oracle finishes
+    in seconds): size-independent properties.  The three ways of stepping it — vec4 with the barrier-chain table
+    (the default), vec4 with barrier cells kept densely in the planes, and the TMA-staged kernel — must agree
+    bit for bit on populations (incl. every barrier cell), moments and curl; the inlet column must not move;
+    total mass of the moment field stays within rounding between two read-outs."""
+    import bench
+    w = h = 16384
+    r0, mask = bench.mask_rows("porous", w, h, 0, h)
+    res = {}
+    for name, kernel, lazy in (("chain", Kernel.Vec4, 1), ("dense", Kernel.Vec4, 0), ("tma", Kernel.Tma, 2)):
+        lbm = LBM(1.0, w, h, inflow_ux=0.05, kernel=kernel, lazy_barriers=lazy)
+        lbm.write_barrier_rows(0, mask)
+        inlet0 = lbm.read_population(5)[:, 0].copy()
+        lbm.iterate(12)
+        rho_a = lbm.reduce_moments()[0]
+        lbm.iterate(13)
+        rho_b = lbm.reduce_moments()[0]
+        assert abs(rho_b - rho_a) < 1e-4 * rho_a
+        assert lbm.lazy_barriers_active() == (lazy != 0)
+        res[name] = [lbm.read_output(), lbm.read_moments()[2]] + [lbm.read_population(k) for k in (1, 4, 6)]
+        assert_same_bits(res[name][2][:, 0], res[name][2][:, 0], "self")
+        assert_same_bits(lbm.read_population(5)[:, 0], inlet0, f"{name}: inlet column e")
+        lbm.close()
+    for other in ("dense", "tma"):
+        for a, b, what in zip(res["chain"], res[other], ("curl", "rho", "n", "rest", "sw")):
+            assert_same_bits(a, b, f"chain vs {other}: {what} at 16384^2")
