@@ -235,8 +235,7 @@ int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale
  * copies; the collision shaders have no mask test), so their state can live in a compact side table that is advanced in
  * registers, which removes their memory traffic from the step kernel.  Results are bit-identical either
- * way.  mode: 0 never, 1 always, 2 auto (default: when >= 2 % of the cells are barriers and a call runs
- * >= 8 steps). */
+ * way.  mode: 0 never, 1 always, 2 auto (default: when >= 2 % of the slab's cells are barriers). */
 int blbm_set_lazy_barriers(blbm_t *h, int mode);
 int blbm_get_lazy_barriers_active(const blbm_t *h);
 /* kernels launched by this handle since creation (the bench's gpu_launches claim) */

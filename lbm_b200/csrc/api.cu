@@ -254,7 +254,7 @@ void stream_free(void *p, cudaStream_t st)
 int chain_try_enter(blbm *h, uint32_t steps_left)
 {
     if (h->chain_active || h->lazy_mode == 0 || h->chain_declined || h->cls_pending) return BLBM_OK;
-    if (h->lazy_mode == 2 && steps_left < 8) return BLBM_OK;
+    (void)steps_left;  // the build pays for itself within a few steps: enter as soon as the mask qualifies
     if (h->plane >= 0xffffffffull) return BLBM_OK;
     CK(launch_chain_count(h->cls[h->cls_cur], geom(h), h->chain_counter, h->mailbox_dev, h->stream));
     h->launches += 2;
