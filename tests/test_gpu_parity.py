@@ -169,12 +169,13 @@ def test_closed_box_cavity_small(kernel):
 
 
 @pytest.mark.parametrize("lazy", LAZY)
-@pytest.mark.parametrize("nslabs", [2, 3])
+@pytest.mark.parametrize("nslabs,size", [(2, (96, 50)), (3, (96, 50)), (2, (97, 41)), (4, (131, 23))])
 @pytest.mark.parametrize("kernel", KERNELS)
-def test_slab_group_on_one_device_matches_single_domain(kernel, nslabs, lazy):
+def test_slab_group_on_one_device_matches_single_domain(kernel, nslabs, size, lazy):
     """y-slab decomposition with direct halo stores, all slabs on cuda:0: must be bit-identical to the
-    undivided lattice (and hence to the oracle), including paints on slab boundaries."""
-    w, h = 96, 50
+    undivided lattice (and hence to the oracle), including paints on slab boundaries; ragged row lengths and
+    uneven slab heights included."""
+    w, h = size
     rng = np.random.default_rng(77 + nslabs)
     grp = SlabGroup(omega_from_viscosity(0.02), w, h, devices=[0] * nslabs, kernel=kernel, lazy_barriers=lazy)
     ora = Oracle(omega_from_viscosity(0.02), w, h)
