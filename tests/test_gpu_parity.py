@@ -261,3 +261,48 @@ def test_full_size_properties_16384_porous():
     for other in ("dense", "tma"):
         for a, b, what in zip(res["chain"], res[other], ("curl", "rho", "n", "rest", "sw")):
             assert_same_bits(a, b, f"chain vs {other}: {what} at 16384^2")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_against_committed_golden_fixture(kernel):
+    """The CUDA path against tests/golden/small_cylinder_64x32.npz (generated by make_golden.py from the oracle
+    and committed), i.e. independently of the oracle build of the day."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_cylinder_64x32.npz"))
+    w, h = 64, 32
+    lbm = LBM(omega_from_viscosity(0.02), w, h, kernel=kernel)
+    lbm.draw_points(disc_pairs(w, 16, 16, 4))
+    lbm.iterate(120)
+    lbm.draw_points(disc_pairs(w, 40, 10, 3))
+    lbm.iterate(80)
+    lbm.update_omega_buffer(1.6)
+    lbm.draw_points(disc_pairs(w, 16, 16, 4, val=0))
+    lbm.iterate(50)
+    for b in (0, 1):
+        for k in range(9):
+            assert_same_bits(lbm.read_population(k, b), g[f"f{b}_{k}"], f"golden f{b}_{k}")
+    mx, my, rho = lbm.read_moments()
+    assert_same_bits(mx, g["mx"], "golden mx")
+    assert_same_bits(my, g["my"], "golden my")
+    assert_same_bits(rho, g["rho"], "golden rho")
+    assert_same_bits(lbm.read_output(), g["out"], "golden out")
+    assert_same_bits(lbm.read_barrier(), g["bar"], "golden bar")
+    assert_same_bits(lbm.read_cell_class(), g["cls"], "golden cls")
+    lbm.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_every_single_cell_preset(kernel):
+    """LBM::single_cell(0..8) (lbm.rs:1482-1515) plus an out-of-range index, each followed by a few steps."""
+    w, h = 72, 40
+    lbm, ora = LBM(1.0 / (3 * 0.1 + 0.5), w, h, kernel=kernel), Oracle(1.0 / (3 * 0.1 + 0.5), w, h)
+    lbm.iterate(3)
+    ora.iterate(3)
+    for idx in list(range(9)) + [12]:
+        lbm.single_cell(idx)
+        ora.single_cell(idx)
+        compare_state(lbm, ora, f"single_cell({idx}) fresh")
+        lbm.iterate(11)
+        ora.iterate(11)
+        compare_state(lbm, ora, f"single_cell({idx}) +11")
+    lbm.close()
