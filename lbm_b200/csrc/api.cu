@@ -332,6 +332,7 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     }
     if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
+    if (mode == MODE_COLLIDE_ONLY) h->halo_dirty = false;  // this launch pushed the live buffer's boundary rows
     if (pushes) return signal_peers(h);
     return BLBM_OK;
 }
@@ -353,6 +354,10 @@ int materialise(blbm *h)
     if (rc) return rc;
     h->regimeT = false;
     consume_pending_class(h);
+    // The live buffer now holds S_step in our rows, but our halo rows of that buffer still hold what the
+    // neighbours pushed two steps ago.  The next collide refreshes them (it pushes T_step); anything that
+    // gathers from the live buffer before that (the public stream half-step) must re-exchange first.
+    if (any_peer(h)) h->halo_dirty = true;
     return BLBM_OK;
 }
 
@@ -737,6 +742,9 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= ndev) return fail(BLBM_EINVAL, "device %d out of range [0,%d)", device, ndev);
     CK(cudaSetDevice(device));
+    CK(preload_aux_kernels());
+    CK(preload_step_kernels());
+    CK(preload_tma_kernels());
 
     blbm *h = new (std::nothrow) blbm();
     if (!h) return fail(BLBM_ENOMEM, "out of host memory");

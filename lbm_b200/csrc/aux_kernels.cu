@@ -710,3 +710,45 @@ cudaError_t launch_color_map(const float *out, const uint8_t *mask, float *rgb, 
 }
 
 }  // namespace blbmk
+
+// ---- eager module loading ---------------------------------------------------------------------------
+// CUDA loads kernels lazily, and loading one may wait for the device to go idle.  Linked slabs keep a
+// spinning wait kernel on the device until the neighbour signals, so a first-use load on the host thread that
+// must enqueue that very signal would deadlock (until the wait times out).  Touch every kernel once up front.
+namespace blbmk {
+#define BLBM_TOUCH(k)                                                    \
+    do {                                                                 \
+        cudaFuncAttributes a__;                                          \
+        cudaError_t e__ = cudaFuncGetAttributes(&a__, k);                \
+        if (e__ != cudaSuccess) return e__;                              \
+    } while (0)
+
+cudaError_t preload_aux_kernels()
+{
+    BLBM_TOUCH(fill_rows_kernel);
+    BLBM_TOUCH(mask_init_kernel);
+    BLBM_TOUCH(mask_scatter_kernel);
+    BLBM_TOUCH(build_class_kernel<false>);
+    BLBM_TOUCH(build_class_kernel<true>);
+    BLBM_TOUCH(precollision_moments_kernel);
+    BLBM_TOUCH(summary_kernel<0>);
+    BLBM_TOUCH(summary_kernel<1>);
+    BLBM_TOUCH(summary_kernel<2>);
+    BLBM_TOUCH(summary_kernel<3>);
+    BLBM_TOUCH(summary_kernel<4>);
+    BLBM_TOUCH(reduce_kernel);
+    BLBM_TOUCH(signal_kernel);
+    BLBM_TOUCH(wait_kernel);
+    BLBM_TOUCH(chain_count_kernel);
+    BLBM_TOUCH(mailbox_kernel);
+    BLBM_TOUCH(chain_build_kernel);
+    BLBM_TOUCH(chain_flush_kernel);
+    BLBM_TOUCH(chain_mark_kernel);
+    BLBM_TOUCH(chain_evict_kernel);
+    BLBM_TOUCH(chain_unmark_kernel);
+    BLBM_TOUCH(chain_replay_kernel);
+    BLBM_TOUCH(color_map_kernel);
+    return cudaSuccess;
+}
+#undef BLBM_TOUCH
+}  // namespace blbmk

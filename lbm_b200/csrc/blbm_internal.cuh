@@ -144,6 +144,11 @@ __device__ __forceinline__ void precollision_moments(const float (&f)[8], float 
 
 enum StepMode { MODE_FUSED = 0, MODE_COLLIDE_ONLY = 1, MODE_STREAM_ONLY = 2 };
 
+// force the lazy module load of every kernel of the library (see aux_kernels.cu)
+cudaError_t preload_aux_kernels();
+cudaError_t preload_step_kernels();
+cudaError_t preload_tma_kernels();
+
 // launchers (kernels.cu)
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
 cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, bool dense_obstacles,

@@ -272,4 +272,38 @@ cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, int block_
     }
 }
 
+// see preload_aux_kernels(): force the (lazy) load of every step-kernel instantiation
+#define BLBM_TOUCH(...)                                                  \
+    do {                                                                 \
+        cudaFuncAttributes a__;                                          \
+        cudaError_t e__ = cudaFuncGetAttributes(&a__, __VA_ARGS__);      \
+        if (e__ != cudaSuccess) return e__;                              \
+    } while (0)
+
+template <int ROWS>
+static cudaError_t touch_vec4_rows()
+{
+    BLBM_TOUCH(step_vec4_kernel<false, ROWS, false>);
+    BLBM_TOUCH(step_vec4_kernel<true, ROWS, false>);
+    BLBM_TOUCH(step_vec4_kernel<false, ROWS, true>);
+    BLBM_TOUCH(step_vec4_kernel<true, ROWS, true>);
+    return cudaSuccess;
+}
+
+cudaError_t preload_step_kernels()
+{
+    BLBM_TOUCH(step_scalar_kernel<MODE_FUSED, false>);
+    BLBM_TOUCH(step_scalar_kernel<MODE_FUSED, true>);
+    BLBM_TOUCH(step_scalar_kernel<MODE_COLLIDE_ONLY, false>);
+    BLBM_TOUCH(step_scalar_kernel<MODE_COLLIDE_ONLY, true>);
+    BLBM_TOUCH(step_scalar_kernel<MODE_STREAM_ONLY, false>);
+    cudaError_t e;
+    if ((e = touch_vec4_rows<1>()) != cudaSuccess) return e;
+    if ((e = touch_vec4_rows<2>()) != cudaSuccess) return e;
+    if ((e = touch_vec4_rows<4>()) != cudaSuccess) return e;
+    if ((e = touch_vec4_rows<8>()) != cudaSuccess) return e;
+    return touch_vec4_rows<16>();
+}
+#undef BLBM_TOUCH
+
 }  // namespace blbmk

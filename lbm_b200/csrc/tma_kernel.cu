@@ -342,4 +342,24 @@ cudaError_t launch_step_tma(const StepParams &p, int mode, bool mom, const void 
     return launch_tma_cfg<4, 2>(p, maps, mom, ctas_per_sm, st);
 }
 
+template <int TY, int STAGES>
+static cudaError_t touch_tma()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, step_tma_kernel<false, TY, STAGES>);
+    if (e != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&a, step_tma_kernel<true, TY, STAGES>);
+}
+
+// see preload_aux_kernels()
+cudaError_t preload_tma_kernels()
+{
+    cudaError_t e;
+    if ((e = touch_tma<8, 4>()) != cudaSuccess) return e;
+    if ((e = touch_tma<8, 2>()) != cudaSuccess) return e;
+    if ((e = touch_tma<4, 4>()) != cudaSuccess) return e;
+    if ((e = touch_tma<4, 3>()) != cudaSuccess) return e;
+    return touch_tma<4, 2>();
+}
+
 }  // namespace blbmk

@@ -437,6 +437,13 @@ class SlabGroup:
     def _all(self, name, *a):
         return [getattr(s, name)(*a) for s in self.slabs]
 
+    def advance(self, n, chunk=32):
+        left = int(n)
+        while left > 0:
+            c = min(chunk, left)
+            self._all("advance", c)
+            left -= c
+
     def iterate(self, n, chunk=32):
         # interleave the slabs' launch queues: a slab's stream waits on its neighbours every step, so
         # never enqueue one slab far ahead of the others from a single host thread

@@ -306,3 +306,94 @@ def test_every_single_cell_preset(kernel):
         ora.iterate(11)
         compare_state(lbm, ora, f"single_cell({idx}) +11")
     lbm.close()
+
+
+def _fuzz(lbm, ora, rng, w, h, tag, tunable, nops=120):
+    n_cmp = 0
+    for it in range(nops):
+        op = int(rng.integers(0, 16))
+        if not tunable and op in (9, 10, 11):
+            op = 0
+        if op <= 4:
+            n = int(rng.integers(1, 30))
+            lbm.iterate(n)
+            ora.iterate(n)
+        elif op == 5:
+            n = int(rng.integers(1, 12))
+            lbm.advance(n)
+            for _ in range(n):
+                ora.step()
+        elif op in (6, 7):
+            m = int(rng.integers(1, 40))
+            loc = rng.integers(0, w * h, size=m)
+            if rng.random() < 0.5:  # a blob, likely to hit existing barrier cells too
+                y0, x0 = int(rng.integers(1, h - 1)), int(rng.integers(1, w - 4))
+                loc = np.array([(y0 + dy) * w + x0 + dx for dy in (0, 1) for dx in range(4) if y0 + dy < h])
+            val = rng.integers(0, 2, size=loc.size) if rng.random() < 0.5 else np.ones(loc.size, np.int64)
+            pairs = np.stack([loc, val], 1).astype(np.uint32)
+            lbm.draw_points(pairs)
+            ora.draw_points(pairs)
+        elif op == 8:
+            o2 = float(rng.uniform(0.6, 1.7))
+            lbm.update_omega_buffer(o2)
+            ora.update_omega_buffer(o2)
+        elif op == 9:
+            lbm.set_kernel(int(rng.integers(1, 4)))
+        elif op == 10:
+            lbm.set_lazy_barriers(int(rng.integers(0, 3)))
+        elif op == 11:
+            knob = int(rng.integers(0, 6))
+            val = {0: [1, 2, 4, 8, 16], 1: [4, 8], 2: [2, 3, 4], 3: [1, 2, 3], 4: [-1, 0, 1], 5: [-1, 0, 1]}[knob]
+            lbm.set_tuning(knob, int(rng.choice(val)))
+        elif op == 12:
+            s = int(rng.integers(0, 5))
+            lbm.compute_summary(s)
+            ora.compute_summary(s)
+        elif op == 13:
+            which = int(rng.integers(0, 4))
+            if which == 0:
+                lbm.collide(); ora.collide()
+            elif which == 1:
+                lbm.stream(); ora.stream()
+            elif which == 2:
+                u = float(rng.uniform(0.0, 0.12))
+                lbm.custom_speed(u); ora.custom_speed(u)
+            else:
+                lbm.reset_barrier(); ora.reset_barrier()
+        elif op == 14:
+            k = int(rng.integers(0, 9))
+            a = lbm.read_population(k)  # a read-back in the middle (materialises, flushes the chain table)
+            assert_same_bits(a, ora.population(-1, k), f"{tag} it {it} pop {k}")
+        else:
+            mx, _, _ = lbm.read_moments()
+            assert_same_bits(mx, ora.moments()[0], f"{tag} it {it} mx")
+        if it % 7 == 6:
+            n_cmp += 1
+            compare_state(lbm, ora, f"{tag} op#{it}")
+    compare_state(lbm, ora, f"{tag} final")
+    assert n_cmp >= nops // 8
+    lbm.close()
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_api_fuzz_against_oracle(seed):
+    """Random walks through the whole API surface — steps of random length, paints (several before a step, on
+    barrier cells, erases), omega changes, resets, half-steps, read-backs at arbitrary points — interleaved with
+    changes that must never alter results: kernel implementation, barrier-chain mode, launch-shape knobs, CUDA
+    graphs.  Compared with the oracle on everything after every few operations."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(40, 140)), int(rng.integers(12, 40))
+    om = omega_from_viscosity(0.05)
+    _fuzz(LBM(om, w, h), Oracle(om, w, h), rng, w, h, f"fuzz seed {seed}", tunable=True)
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 24, 25, 26, 27, 28])
+def test_api_fuzz_slab_group(seed):
+    """The same random walk over a lattice split into 2-4 linked slabs on cuda:0."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(40, 140)), int(rng.integers(16, 40))
+    om = omega_from_viscosity(0.05)
+    nslabs = int(rng.integers(2, 5))
+    grp = SlabGroup(om, w, h, devices=[0] * nslabs, kernel=Kernel(int(rng.integers(1, 4))),
+                    lazy_barriers=int(rng.integers(0, 3)))
+    _fuzz(grp, Oracle(om, w, h), rng, w, h, f"slab fuzz seed {seed} x{nslabs}", tunable=False, nops=80)
