@@ -229,7 +229,8 @@ typedef enum blbm_tune {
     BLBM_TUNE_TMA_STAGES = 2,      /* depth of the shared-memory ring: 2..4 (default 4) */
     BLBM_TUNE_TMA_CTAS_PER_SM = 3, /* persistent CTAs per SM: 1..8 (default 2) */
     BLBM_TUNE_VEC4_DENSE = 4,      /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles */
-    BLBM_TUNE_CUDA_GRAPHS = 5      /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
+    BLBM_TUNE_CUDA_GRAPHS = 5,     /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
+    BLBM_TUNE_VEC4_PACKED = 6      /* collide cell pairs with packed fp32 adds (sm_100 FADD2): 1 (default) or 0; same bits */
 } blbm_tune;
 int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale

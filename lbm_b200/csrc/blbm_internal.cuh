@@ -128,6 +128,117 @@ __device__ __forceinline__ void collide_cell(float (&f)[8], float &rest, const f
 #undef BLBM_RELAX
 }
 
+// ---- the same collision on TWO cells at once with Blackwell's packed fp32 adds -------------------------
+// sm_100 has add/sub/mul/fma on f32x2 register pairs (SASS FADD2/FMUL2/FFMA2): one issue slot, two individually
+// rounded fp32 results.  Every add and sub of collide_cell() is done packed here (62 of the 94 fp32 ops per
+// cell), which removes a quarter of the step kernel's instructions at bit-identical results.  The multiplies
+// stay scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 (and even fma.rn.f32x2 with a -0.0 addend)
+// followed by add/sub.rn.f32x2 into one FFMA2 although the roundings are explicit, which would break the
+// "every op individually rounded" contract; scalar FMUL feeding FADD2 is never contracted (the build checks
+// the SASS of the step kernels for FFMA2/FMUL2: `make sass-check`).  lo half = first cell, hi half = second.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(const float lo, const float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(const f32x2_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t add2(const f32x2_t a, const f32x2_t b)
+{
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t sub2(const f32x2_t a, const f32x2_t b)
+{
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t mul2(const f32x2_t a, const f32x2_t b)
+{
+    float al, ah, bl, bh;
+    upk2(a, al, ah);
+    upk2(b, bl, bh);
+    return pk2(__fmul_rn(al, bl), __fmul_rn(ah, bh));
+}
+__device__ __forceinline__ f32x2_t mulc2(const float c, const f32x2_t a)
+{
+    float al, ah;
+    upk2(a, al, ah);
+    return pk2(__fmul_rn(c, al), __fmul_rn(c, ah));
+}
+__device__ __forceinline__ f32x2_t div2(const f32x2_t a, const f32x2_t b)
+{
+    float al, ah, bl, bh;
+    upk2(a, al, ah);
+    upk2(b, bl, bh);
+    return pk2(__fdiv_rn(al, bl), __fdiv_rn(ah, bh));
+}
+
+// collide_cell() on the cell pair held in the lo/hi halves; same operations in the same association
+__device__ __forceinline__ void collide_pair(f32x2_t (&f)[8], f32x2_t &rest, const float omega, f32x2_t &mx,
+                                             f32x2_t &my, f32x2_t &rho)
+{
+    const f32x2_t nw = f[D_NW], n = f[D_N], ne = f[D_NE], w = f[D_W], e = f[D_E], sw = f[D_SW], s = f[D_S],
+                  se = f[D_SE];
+    const f32x2_t one = pk2(1.0f, 1.0f);
+    f32x2_t m_x = sub2(sub2(add2(ne, se), nw), sw);
+    f32x2_t m_y = sub2(sub2(add2(ne, nw), se), sw);
+    f32x2_t r = add2(add2(add2(ne, se), nw), sw);
+    m_x = add2(m_x, sub2(e, w));
+    m_y = add2(m_y, sub2(n, s));
+    r = add2(r, add2(add2(add2(e, n), s), w));
+    r = add2(r, rest);
+    mx = m_x;
+    my = m_y;
+    rho = r;
+    const f32x2_t ux = div2(m_x, r), uy = div2(m_y, r);
+    const f32x2_t k36 = mulc2(1.0f / 36.0f, r), k9 = mulc2(1.0f / 9.0f, r), k49 = mulc2(4.0f / 9.0f, r);
+    const f32x2_t ux3 = mulc2(3.0f, ux), uy3 = mulc2(3.0f, uy);
+    const f32x2_t ux2 = mul2(ux, ux), uy2 = mul2(uy, uy);
+    const f32x2_t uxuy2 = mul2(mulc2(2.0f, ux), uy);
+    const f32x2_t u2 = add2(ux2, uy2);
+    const f32x2_t u215 = mulc2(1.5f, u2);
+    const f32x2_t one_p_ux3 = add2(one, ux3), one_m_ux3 = sub2(one, ux3);
+    const f32x2_t q_pos = mulc2(4.5f, add2(u2, uxuy2)), q_neg = mulc2(4.5f, sub2(u2, uxuy2));
+#define BLBM_RELAX2(fi, k, poly) add2(fi, mulc2(omega, sub2(mul2(k, sub2(poly, u215)), fi)))
+    f[D_NE] = BLBM_RELAX2(ne, k36, add2(add2(one_p_ux3, uy3), q_pos));
+    f[D_SE] = BLBM_RELAX2(se, k36, add2(sub2(one_p_ux3, uy3), q_neg));
+    f[D_NW] = BLBM_RELAX2(nw, k36, add2(add2(one_m_ux3, uy3), q_neg));
+    f[D_SW] = BLBM_RELAX2(sw, k36, add2(sub2(one_m_ux3, uy3), q_pos));
+    rest = add2(rest, mulc2(omega, sub2(mul2(k49, sub2(one, u215)), rest)));
+    const f32x2_t ax = mulc2(4.5f, ux2), ay = mulc2(4.5f, uy2);
+    f[D_E] = BLBM_RELAX2(e, k9, add2(one_p_ux3, ax));
+    f[D_W] = BLBM_RELAX2(w, k9, add2(one_m_ux3, ax));
+    f[D_N] = BLBM_RELAX2(n, k9, add2(add2(one, uy3), ay));
+    f[D_S] = BLBM_RELAX2(s, k9, add2(sub2(one, uy3), ay));
+#undef BLBM_RELAX2
+}
+
+// four consecutive cells g[q][d], q = 0..3: two packed pair collisions, results back in the scalar arrays
+__device__ __forceinline__ void collide_quad_packed(float (&g)[4][8], float (&rr)[4], const float omega,
+                                                    float (&mx)[4], float (&my)[4], float (&rho)[4])
+{
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        f32x2_t f[8], rest = pk2(rr[2 * h], rr[2 * h + 1]), pmx, pmy, prho;
+#pragma unroll
+        for (int d = 0; d < 8; d++) f[d] = pk2(g[2 * h][d], g[2 * h + 1][d]);
+        collide_pair(f, rest, omega, pmx, pmy, prho);
+#pragma unroll
+        for (int d = 0; d < 8; d++) upk2(f[d], g[2 * h][d], g[2 * h + 1][d]);
+        upk2(rest, rr[2 * h], rr[2 * h + 1]);
+        upk2(pmx, mx[2 * h], mx[2 * h + 1]);
+        upk2(pmy, my[2 * h], my[2 * h + 1]);
+        upk2(prho, rho[2 * h], rho[2 * h + 1]);
+    }
+}
+
 // moments exactly as the two pre-collision passes leave them (no rest term): reset_to_equilibrium /
 // custom_speed, lbm.rs:1076-1102
 __device__ __forceinline__ void precollision_moments(const float (&f)[8], float &mx, float &my, float &rho)
@@ -152,7 +263,7 @@ cudaError_t preload_tma_kernels();
 // launchers (kernels.cu)
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
 cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, bool dense_obstacles,
-                             cudaStream_t st);
+                             bool packed, cudaStream_t st);
 
 // TMA-staged variant (tma_kernel.cu).  The tensor maps are opaque 128-byte blobs owned by the handle:
 // 16 population maps (buffer-major, Dir order) and one for the rest plane, encoded for `tile_rows`.

@@ -31,7 +31,8 @@ __device__ __forceinline__ bool reloads_own(const uint32_t c)
 
 // g[q][d]: gathered (pulled, bounce-back already applied) populations of cells x4+q, q = 0..3, at plane
 // offset i; c0..c3 their class words; vr their rest populations.
-template <bool MOM>
+// PACKED: collide the four cells as two pairs with packed fp32 adds (collide_pair, blbm_internal.cuh).
+template <bool MOM, bool PACKED = false>
 __device__ __forceinline__ void finish_group(const StepParams &p, const size_t i, const uint32_t x4, const uint32_t r,
                                              float (&g)[4][8], const uint32_t c0, const uint32_t c1,
                                              const uint32_t c2, const uint32_t c3, const float4 vr)
@@ -74,8 +75,12 @@ __device__ __forceinline__ void finish_group(const StepParams &p, const size_t i
 
     float rr[4] = {vr.x, vr.y, vr.z, vr.w};
     float mx[4], my[4], rho[4];
+    if (PACKED) {
+        collide_quad_packed(g, rr, p.omega, mx, my, rho);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], p.omega, mx[q], my[q], rho[q]);
+        for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], p.omega, mx[q], my[q], rho[q]);
+    }
 
     // cells beyond the row end (ragged W) are padding: written, never read
     stg4(p.R + i, make_float4(rr[0], rr[1], rr[2], rr[3]));

@@ -83,3 +83,18 @@ def test_slab_rows_partition():
         assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
         sizes = [b - a for a, b in r]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_packed_adds_are_never_contracted_into_packed_fmas():
+    """The step kernels collide cell pairs with sm_100's packed fp32 adds (FADD2).  ptxas 12.9 contracts
+    mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the explicit roundings, so the multiplies stay scalar; the
+    shipped SASS must hold packed adds and no packed multiply / multiply-add (parity contract: every op
+    individually rounded)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lbm_b200.library_path()], capture_output=True, text=True).stdout
+    assert "FADD2" in sass
+    assert "FFMA2" not in sass and "FMUL2" not in sass
