@@ -9,7 +9,6 @@
 // iterate(n) leaves the handle in the T-regime; anything that must observe or perturb the reference's
 // buffers (read/write population, the public half-steps) materialises first.
 #include <algorithm>
-#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -84,11 +83,6 @@ struct blbm_handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_sum = nullptr, ev_copy = nullptr;
     bool copy_pending = false;
-    // side stream for the barrier-chain replay (compute-bound, independent of the planes): it runs beside the
-    // HBM-bound step launches of the same call and is joined before the moment-storing launch
-    cudaStream_t chain_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_chain = nullptr;
-    bool chain_inflight = false;
     uint32_t W = 0, P = 0, rows = 0;
     uint64_t Hg = 0, row0 = 0, row1 = 0;
     size_t plane = 0;  // elements per population plane, (rows+3)*P
@@ -436,50 +430,7 @@ int run_step_graph(blbm *h)
     return BLBM_OK;
 }
 
-// Streams of one process share the device's hardware work queues (8 by default); beyond that, a slab's
-// spinning wait kernel can end up queued in front of the very signal kernel it waits for.  Side streams are
-// therefore only created while the process stays within that budget.
-std::atomic<int> g_streams{0};
-constexpr int STREAM_BUDGET = 8;
-
-cudaStream_t chain_side_stream(blbm *h)
-{
-    if (h->chain_stream) return h->chain_stream;
-    if (g_streams.fetch_add(1) >= STREAM_BUDGET) {
-        g_streams.fetch_sub(1);
-        return nullptr;
-    }
-    if (cudaStreamCreateWithFlags(&h->chain_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_chain, cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError();
-        if (h->chain_stream) cudaStreamDestroy(h->chain_stream);
-        h->chain_stream = nullptr;
-        g_streams.fetch_sub(1);
-        return nullptr;
-    }
-    return h->chain_stream;
-}
-
-// the main stream continues only after the side-stream replay of this call has finished
-int join_chain_replay(blbm *h)
-{
-    if (!h->chain_inflight) return BLBM_OK;
-    h->chain_inflight = false;
-    CK(cudaStreamWaitEvent(h->stream, h->ev_chain, 0));
-    return BLBM_OK;
-}
-
-int do_steps_unjoined(blbm *h, uint32_t n);
-
 int do_steps(blbm *h, uint32_t n)
-{
-    const int rc = do_steps_unjoined(h, n);
-    const int rj = join_chain_replay(h);
-    return rc ? rc : rj;
-}
-
-int do_steps_unjoined(blbm *h, uint32_t n)
 {
     uint32_t left = n;
     bool replayed = false;
@@ -491,22 +442,11 @@ int do_steps_unjoined(blbm *h, uint32_t n)
         if (h->chain_active && !replayed) {
             // barrier cells do not depend on anything else: advance their chains through all the steps of
             // this call up front, in registers; this also stores the moments of the call's last collide
-            cudaStream_t cs = left > 2 ? chain_side_stream(h) : nullptr;
-            if (cs) {
-                CK(cudaEventRecord(h->ev_fork, h->stream));
-                CK(cudaStreamWaitEvent(cs, h->ev_fork, 0));
-            }
             CK(launch_chain_replay(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, left,
-                                   (uint32_t)(h->step % 2), h->omega, h->mx, h->my, h->rho, cs ? cs : h->stream));
+                                   (uint32_t)(h->step % 2), h->omega, h->mx, h->my, h->rho, h->stream));
             h->launches++;
-            if (cs) {
-                CK(cudaEventRecord(h->ev_chain, cs));
-                h->chain_inflight = true;
-            }
             replayed = true;
         }
-        // the moment-storing launch keeps the moments the replay stored at chain cells
-        if (mom && (rc = join_chain_replay(h)) != BLBM_OK) return rc;
         if (graphs && h->regimeT && !h->cls_pending && left > GRAPH_CHUNK) {
             if ((rc = run_step_graph(h)) != BLBM_OK) return rc;
             left -= GRAPH_CHUNK;
@@ -871,7 +811,6 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
             (ce = cudaHostGetDevicePointer((void **)&h->mailbox_dev, h->mailbox_host, 0)) != cudaSuccess ||
             (ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-            (g_streams.fetch_add(2), false) ||
             (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
             (ce = cudaEventCreateWithFlags(&h->ev_sum, cudaEventDisableTiming)) != cudaSuccess ||
             (ce = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
@@ -925,17 +864,9 @@ int blbm_destroy(blbm_t *h)
         if (h->graph[q].exec) cudaGraphExecDestroy(h->graph[q].exec);
     if (h->mailbox_host) cudaFreeHost(h->mailbox_host);
     if (h->pool) cudaFree(h->pool);
-    if (h->chain_stream) {
-        cudaStreamSynchronize(h->chain_stream);
-        cudaStreamDestroy(h->chain_stream);
-        g_streams.fetch_sub(1);
-    }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_chain) cudaEventDestroy(h->ev_chain);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamDestroy(h->copy_stream);
-        g_streams.fetch_sub(2);
     }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
