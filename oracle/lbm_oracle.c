@@ -5,10 +5,17 @@
  * call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and only as the checker / the timed CPU arm.
  *
- * PARITY UNPINNED: the reference (PPLUSCHT/LBM) ships no tests, golden vectors or read-back path, and
- * cannot be built here (Rust -> wasm32 + browser WebGPU; no cargo / Vulkan / lavapipe in the image), so
- * this oracle is pinned only by (a) an op-for-op reading of the WGSL below, (b) an independent numpy
- * restatement (oracle/lbm_numpy.py) that must agree bit-for-bit, (c) analytic known-answer tests.
+ * PARITY STATUS: the reference (PPLUSCHT/LBM) ships no tests, golden vectors or read-back path, and
+ * cannot be built or run here (Rust -> wasm32 + browser WebGPU; no cargo / Vulkan / lavapipe in the image),
+ * so no output of an actual wgpu execution exists: in that strict sense parity is UNPINNED.  What pins this
+ * oracle instead: (a) the reference's own WGSL shader text, parsed and executed invocation by invocation by
+ * oracle/wgsl_interp.py, produced tests/golden/wgsl_golden.npz (random API scripts, config-1 miniatures,
+ * porous mask, single_cell presets, paints on every special cell class, every summary statistic and colour
+ * map); this file must reproduce those buffers bit for bit (tests/test_wgsl_pin.py), so the arithmetic,
+ * association, guards and index helpers are pinned to the reference's source, with only the host-side
+ * dispatch order restated from lbm.rs; (b) an independent numpy restatement (oracle/lbm_numpy.py) that must
+ * agree bit for bit; (c) analytic known-answer tests.  Not pinned by anything: what a particular WebGPU
+ * backend does where WGSL leaves room (FMA contraction, out-of-range access) -- see the semantics below.
  *
  * The reference's structure is preserved on purpose: 8 passes per step over 2x9 fp32 SoA arrays,
  * three moment arrays and a u32 barrier mask, every intermediate going through fp32 memory exactly

@@ -749,6 +749,42 @@ class WgslLBM:
     def reset_to_equilibrium(self):
         self.custom_speed(f32(0.1))
 
+    # -- lbm.rs:1482-1515: set_equil(0,0,1) plus one population set to 4.0 at a fixed cell; no pre-collision
+    def single_cell(self, index):
+        x, y = self.x, self.y
+        init = self.set_equil(f32(0.0), f32(0.0), f32(1.0))
+        vec = [np.full(self.n, init[k], dtype=f32) for k in range(9)]
+        cell = {0: (x - 2, y - 2), 1: (3 * x // 4, y - 2), 2: (x // 3, y - 2), 3: (x - 2, y // 2),
+                4: (3 * x // 4, y // 2), 5: (x // 2, y // 2), 6: (x - 2, 1), 7: (3 * x // 4, 1),
+                8: (x // 2, 1)}.get(int(index))
+        if cell is not None:
+            vec[int(index)][cell[0] + cell[1] * x] = f32(4.0)
+        for b in range(2):
+            for k in range(9):
+                self.data[b][k][:] = vec[k]
+        self.compute_step = 0
+
+    # numeric selectors in the reference's enum order (lbm.rs:10-24): Curl, Ux, Uy, Rho, Speed / Inferno, Viridis, Jet
+    STATS = ("curl", "ux", "uy", "rho", "speed")
+    CMAPS = ("inferno", "viridis", "jet")
+
+    def compute_summary(self, stat):
+        self.summary_stat = self.STATS[int(stat)]
+        self.calculate_summary()
+
+    def colors_of(self, cmap):
+        self.color_map(self.CMAPS[int(cmap)])
+        return self.colors.reshape(self.y, self.x, 3).copy()
+
+    def state(self):
+        """everything observable, as arrays shaped (y, x): 18 populations (rest twice = buffer 0), moments,
+        output, barrier"""
+        shp = (self.y, self.x)
+        st = {f"f{b}_{k}": self.population(b, k).reshape(shp).copy() for b in range(2) for k in range(9)}
+        st.update(mx=self.ux.reshape(shp).copy(), my=self.uy.reshape(shp).copy(), rho=self.rho.reshape(shp).copy(),
+                  out=self.output.reshape(shp).copy(), barrier=self.barrier.reshape(shp).copy())
+        return st
+
     # accessors shaped like oracle/lbm_oracle.py
     def population(self, buffer, k):
         return self.data[0][REST] if k == REST else self.data[buffer][k]
