@@ -212,8 +212,9 @@ def main():
     ap.add_argument("--frame-steps", type=int, default=15, help="steps per frame of the e2e loop (lib.rs:17)")
     ap.add_argument("--block-rows", type=int, default=0, help="vec4 kernel rows per block (4, 8, 16); 0 = default")
     ap.add_argument("--graphs", type=int, default=-1, help="CUDA graphs for the step loop: -1 auto, 0 off, 1 on")
-    ap.add_argument("--dense", type=int, default=-1, help="vec4 bounce flavour: -1 auto, 0 sparse, 1 dense")
+    ap.add_argument("--dense", type=int, default=-1, help="vec4 bounce flavour: -1 auto, 0 sparse, 1 dense, 2 dense + cp.async staging")
     ap.add_argument("--packed", type=int, default=-1, help="vec4 packed fp32 adds (FADD2): -1 default (on), 0, 1")
+    ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 default (on), 0, 1")
     ap.add_argument("--tma-rows", type=int, default=0)
     ap.add_argument("--tma-stages", type=int, default=0)
     ap.add_argument("--tma-ctas", type=int, default=0)
@@ -259,6 +260,8 @@ def main():
         lbm.set_tuning(5, args.graphs)
     if args.packed >= 0:
         lbm.set_tuning(6, args.packed)
+    if args.index32 >= 0:
+        lbm.set_tuning(7, args.index32)
     for knob, val in ((1, args.tma_rows), (2, args.tma_stages), (3, args.tma_ctas)):
         if val:
             lbm.set_tuning(knob, val)

@@ -228,9 +228,13 @@ typedef enum blbm_tune {
     BLBM_TUNE_TMA_TILE_ROWS = 1,   /* rows per TMA tile: 4 (default) or 8 */
     BLBM_TUNE_TMA_STAGES = 2,      /* depth of the shared-memory ring: 2..4 (default 4) */
     BLBM_TUNE_TMA_CTAS_PER_SM = 3, /* persistent CTAs per SM: 1..8 (default 2) */
-    BLBM_TUNE_VEC4_DENSE = 4,      /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles */
+    BLBM_TUNE_VEC4_DENSE = 4,      /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles,
+                                      2 dense + own-row vectors staged in shared memory with cp.async (what auto
+                                      picks wherever the barrier-chain table is active) */
     BLBM_TUNE_CUDA_GRAPHS = 5,     /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
-    BLBM_TUNE_VEC4_PACKED = 6      /* collide cell pairs with packed fp32 adds (sm_100 FADD2): 1 (default) or 0; same bits */
+    BLBM_TUNE_VEC4_PACKED = 6,     /* collide cell pairs with packed fp32 adds (sm_100 FADD2): 0 (default) or 1; same bits,
+                                      measured slower (register pressure) */
+    BLBM_TUNE_VEC4_INDEX32 = 7     /* 32-bit plane offsets where a plane has < 2^32 elements: 1 (default) or 0 */
 } blbm_tune;
 int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale

@@ -262,8 +262,10 @@ cudaError_t preload_tma_kernels();
 
 // launchers (kernels.cu)
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
-cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, bool dense_obstacles,
-                             bool packed, cudaStream_t st);
+// dense_obstacles: 0 sparse fix-up (one branch per direction), 1 branch-free, 2 branch-free + cp.async staging
+// index32: use 32-bit plane offsets where the slab allows it
+cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, int dense_obstacles,
+                             bool packed, bool index32, cudaStream_t st);
 
 // TMA-staged variant (tma_kernel.cu).  The tensor maps are opaque 128-byte blobs owned by the handle:
 // 16 population maps (buffer-major, Dir order) and one for the rest plane, encoded for `tile_rows`.

@@ -32,8 +32,10 @@ __device__ __forceinline__ bool reloads_own(const uint32_t c)
 // g[q][d]: gathered (pulled, bounce-back already applied) populations of cells x4+q, q = 0..3, at plane
 // offset i; c0..c3 their class words; vr their rest populations.
 // PACKED: collide the four cells as two pairs with packed fp32 adds (collide_pair, blbm_internal.cuh).
-template <bool MOM, bool PACKED = false>
-__device__ __forceinline__ void finish_group(const StepParams &p, const size_t i, const uint32_t x4, const uint32_t r,
+// IDX: type of the plane offset i — uint32_t where a plane has fewer than 2^32 elements (one IMAD.WIDE per
+// address instead of a 64-bit add pair), size_t otherwise.
+template <bool MOM, bool PACKED = false, typename IDX = size_t>
+__device__ __forceinline__ void finish_group(const StepParams &p, const IDX i, const uint32_t x4, const uint32_t r,
                                              float (&g)[4][8], const uint32_t c0, const uint32_t c1,
                                              const uint32_t c2, const uint32_t c3, const float4 vr)
 {
@@ -58,7 +60,7 @@ __device__ __forceinline__ void finish_group(const StepParams &p, const size_t i
             if (j < 4) {
                 const uint32_t cj = j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3));
                 if (!(cj & CLS_SKIP)) {
-                    const size_t ij = i + j;
+                    const size_t ij = (size_t)i + j;
 #pragma unroll
                     for (int d = 0; d < 8; d++) {
                         if (dir_dx(d) < 0 && !(cj & cls_upstream_bit(d))) {

@@ -152,6 +152,28 @@ def test_porous_channel_small(kernel, lazy):
 
 
 @pytest.mark.parametrize("lazy", [0, 1])
+@pytest.mark.parametrize("flavour", [1, 2])
+@pytest.mark.parametrize("rows", [1, 4, 16])
+@pytest.mark.parametrize("size", [(256, 128), (131, 23), (5, 4)])
+def test_staged_bounce_back_bit_exact(size, rows, lazy, flavour):
+    """BLBM_TUNE_VEC4_DENSE = 2: the own-row vectors of the bounce-back staged in shared memory with cp.async."""
+    w, h = size
+    lbm = LBM(1.0, w, h, inflow_ux=0.05, kernel=Kernel.Vec4, lazy_barriers=lazy)
+    lbm.set_tuning(4, flavour)
+    lbm.set_tuning(0, rows)
+    ora = Oracle(1.0, w, h, inflow_ux=0.05)
+    pts = porous_pairs(w, h)
+    if len(pts):
+        lbm.draw_points(pts)
+        ora.draw_points(pts.astype(np.uint32))
+    for n in (1, 2, 60, 201):
+        lbm.iterate(n)
+        ora.iterate(n)
+        compare_state(lbm, ora, f"staged {w}x{h} rows={rows} +{n}")
+    lbm.close()
+
+
+@pytest.mark.parametrize("lazy", [0, 1])
 @pytest.mark.parametrize("size", [(256, 128), (131, 23)])
 def test_packed_add_collision_bit_exact(size, lazy):
     """BLBM_TUNE_VEC4_PACKED: the collision of cell pairs with sm_100's packed fp32 adds (FADD2) gives the same
@@ -361,9 +383,9 @@ def _fuzz(lbm, ora, rng, w, h, tag, tunable, nops=120):
         elif op == 10:
             lbm.set_lazy_barriers(int(rng.integers(0, 3)))
         elif op == 11:
-            knob = int(rng.integers(0, 7))
-            val = {0: [1, 2, 4, 8, 16], 1: [4, 8], 2: [2, 3, 4], 3: [1, 2, 3], 4: [-1, 0, 1], 5: [-1, 0, 1],
-                   6: [0, 1]}[knob]
+            knob = int(rng.integers(0, 8))
+            val = {0: [1, 2, 4, 8, 16], 1: [4, 8], 2: [2, 3, 4], 3: [1, 2, 3], 4: [-1, 0, 1, 2], 5: [-1, 0, 1],
+                   6: [0, 1], 7: [0, 1]}[knob]
             lbm.set_tuning(knob, int(rng.choice(val)))
         elif op == 12:
             s = int(rng.integers(0, 5))
