@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=-1, help="CUDA graphs for the step loop: -1 auto, 0 off, 1 on")
     ap.add_argument("--dense", type=int, default=-1, help="vec4 bounce flavour: -1 auto, 0 sparse, 1 dense, 2 dense + cp.async staging")
     ap.add_argument("--packed", type=int, default=-1, help="vec4 packed fp32 adds (FADD2): -1 default (on), 0, 1")
-    ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 default (on), 0, 1")
+    ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 auto, 0, 1")
     ap.add_argument("--tma-rows", type=int, default=0)
     ap.add_argument("--tma-stages", type=int, default=0)
     ap.add_argument("--tma-ctas", type=int, default=0)

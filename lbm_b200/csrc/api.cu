@@ -111,7 +111,7 @@ struct blbm_handle {
     int kernel = BLBM_KERNEL_VEC4;
     int vec4_dense = -1;  // bounce-back flavour of the vec4 kernel: -1 auto, 0 sparse, 1 dense
     int vec4_packed = 0;  // 1: collide cell pairs with packed fp32 adds (FADD2): same bits, but measured slower (registers)
-    int vec4_index32 = 1;  // 32-bit plane offsets in the vec4 kernel where a plane has < 2^32 elements
+    int vec4_index32 = -1;  // 32-bit plane offsets in the vec4 kernel (plane < 2^32 elements): -1 auto, 0, 1
     int vec4_rows = 4;  // rows per block of the vec4 kernel (tuning knob; 4 measured best on the porous case)
     // TMA-staged kernel: tensor maps (opaque 128-byte descriptors) and launch shape
     alignas(64) unsigned char tma_maps[16 * 128];
@@ -329,8 +329,13 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     default:
         // the obstacle-dense flavour with cp.async-staged own rows wherever the chain table is in use (>= 2 % barrier
         // cells), unless overridden
-        e = launch_step_vec4(p, mode, mom, h->vec4_rows, h->vec4_dense < 0 ? (h->chain_active ? 2 : 0) : h->vec4_dense,
-                             h->vec4_packed != 0, h->vec4_index32 != 0, h->stream);
+        {
+            const int flavour = h->vec4_dense < 0 ? (h->chain_active ? 2 : 0) : h->vec4_dense;
+            // 32-bit plane offsets pay off in the sparse flavour (64 instead of 72 registers: 2.91 vs 3.13 ms on the
+            // empty 16384^2 channel); the staged dense flavour is faster with 64-bit offsets (no spill: 3.09 vs 3.14)
+            const bool index32 = h->vec4_index32 < 0 ? flavour == 0 : h->vec4_index32 != 0;
+            e = launch_step_vec4(p, mode, mom, h->vec4_rows, flavour, h->vec4_packed != 0, index32, h->stream);
+        }
         break;
     }
     if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
@@ -394,7 +399,7 @@ int run_step_graph(blbm *h)
         1ull + (unsigned long long)h->cls_cur, omega_bits,
         (unsigned long long)h->kernel | ((unsigned long long)h->vec4_rows << 8) |
             ((unsigned long long)(h->vec4_dense + 1) << 16) | ((unsigned long long)h->chain_active << 24) |
-            ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)h->vec4_index32 << 26),
+            ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)(h->vec4_index32 + 1) << 26),
         (unsigned long long)(uintptr_t)h->pool};
     if (!g.exec || memcmp(g.sig, sig, sizeof(sig)) != 0) {
         if (g.exec) {
@@ -1415,7 +1420,7 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
         h->vec4_packed = value;
         return BLBM_OK;
     case BLBM_TUNE_VEC4_INDEX32:
-        if (value != 0 && value != 1) return fail(BLBM_EINVAL, "index32 must be 0 or 1");
+        if (value < -1 || value > 1) return fail(BLBM_EINVAL, "index32 must be -1 (auto), 0 or 1");
         h->vec4_index32 = value;
         return BLBM_OK;
     case BLBM_TUNE_CUDA_GRAPHS:

@@ -385,7 +385,7 @@ def _fuzz(lbm, ora, rng, w, h, tag, tunable, nops=120):
         elif op == 11:
             knob = int(rng.integers(0, 8))
             val = {0: [1, 2, 4, 8, 16], 1: [4, 8], 2: [2, 3, 4], 3: [1, 2, 3], 4: [-1, 0, 1, 2], 5: [-1, 0, 1],
-                   6: [0, 1], 7: [0, 1]}[knob]
+                   6: [0, 1], 7: [-1, 0, 1]}[knob]
             lbm.set_tuning(knob, int(rng.choice(val)))
         elif op == 12:
             s = int(rng.integers(0, 5))
