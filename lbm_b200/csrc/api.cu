@@ -1412,7 +1412,7 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
         h->vec4_rows = value;
         return BLBM_OK;
     case BLBM_TUNE_VEC4_DENSE:
-        if (value < -1 || value > 2) return fail(BLBM_EINVAL, "dense flavour must be -1 (auto), 0, 1 or 2");
+        if (value < -1 || value > 3) return fail(BLBM_EINVAL, "dense flavour must be -1 (auto) or 0..3");
         h->vec4_dense = value;
         return BLBM_OK;
     case BLBM_TUNE_VEC4_PACKED:

@@ -152,7 +152,11 @@ constexpr uint32_t GRID_Y = 32768;
 template <bool MOM, int V4_ROWS, int DENSE, bool PACKED, typename IDX>
 __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? 1024 / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
 {
-    constexpr bool STAGED = DENSE == 2;
+    constexpr bool STAGED = DENSE >= 2;
+    constexpr bool EAGER_CLS = DENSE == 3;  // class words read up front, without the chunk-flag test
+    // sparse flavour: class words read only after the pulls have arrived, inside a warp-uniform branch on the chunk
+    // flag - a predicated load up front makes the in-order issue wait for the flag byte before the remaining pulls
+    constexpr bool LATE_CLS = DENSE == 0;
     __shared__ float4 own_s[STAGED ? 6 : 1][STAGED ? 32 * V4_ROWS : 1];
     const uint32_t tid = threadIdx.y * 32u + threadIdx.x;
     const uint32_t nbx = gridDim.x;  // = ceil(P / 128)
@@ -171,14 +175,16 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? 1024 / (32 * V4_ROWS) : 
     float4 vn, vs, ve, vw, vne, vnw, vse, vsw, vr;
     vn = vs = ve = vw = vne = vnw = vse = vsw = vr = make_float4(0.f, 0.f, 0.f, 0.f);
     // one flag byte per (row, 128-cell chunk) — the same address for the whole warp — tells whether any
-    // class word of the chunk is non-zero; clean chunks never touch the class plane
-    const bool chunk_dirty = p.rowflag[(size_t)r * nbx + bx] != 0;
+    // class word of the chunk is non-zero; clean chunks never touch the class plane.  Issue order matters (the SM
+    // issues in order and a predicated load waits for its predicate): the flag byte is requested first and
+    // consumed LAST, after every independent load of the thread is in flight; the warp-edge floats are requested
+    // with the pulls, not after the shuffles that wait for the pulls.
+    const uint8_t flag = EAGER_CLS ? (uint8_t)1 : p.rowflag[(size_t)r * nbx + bx];
+    float le = 0.f, lne = 0.f, lse = 0.f, rw = 0.f, rnw = 0.f, rsw = 0.f;
+    const bool edge_l = valid && lane == 0 && x4 != 0;
+    const bool edge_r = valid && lane == 31;  // x4+4 <= P: still inside the row pitch (or x=0 of the next row: unused)
     if (valid) {
-        if (STAGED) {
-#pragma unroll
-            for (int q = 0; q < 6; q++) cp_async16(&own_s[q][tid], p.X[stage_dir(q)] + i);
-        }
-        if (chunk_dirty) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
+        if (EAGER_CLS) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
         vn = ldg4(p.X[D_N] + i + P);
         vne = ldg4(p.X[D_NE] + i + P);
         vnw = ldg4(p.X[D_NW] + i + P);
@@ -188,23 +194,44 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? 1024 / (32 * V4_ROWS) : 
         vse = ldg4(p.X[D_SE] + i - P);
         vsw = ldg4(p.X[D_SW] + i - P);
         vr = ldg4(p.R + i);
+        if (edge_l) {
+            le = p.X[D_E][i - 1];
+            lne = p.X[D_NE][i + P - 1];
+            lse = p.X[D_SE][i - P - 1];
+        }
+        if (edge_r) {
+            rw = p.X[D_W][i + 4];
+            rnw = p.X[D_NW][i + P + 4];
+            rsw = p.X[D_SW][i - P + 4];
+        }
+        if (STAGED) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) cp_async16(&own_s[q][tid], p.X[stage_dir(q)] + i);
+        } else {
+            asm volatile("" ::: "memory");  // keep the class-word load below behind the loads above
+        }
+        if (!EAGER_CLS && !LATE_CLS && flag != 0) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
     }
-    // element x4-1 of the east-moving populations, element x4+4 of the west-moving ones
-    float le = __shfl_up_sync(FULL, ve.w, 1), lne = __shfl_up_sync(FULL, vne.w, 1),
-          lse = __shfl_up_sync(FULL, vse.w, 1);
-    float rw = __shfl_down_sync(FULL, vw.x, 1), rnw = __shfl_down_sync(FULL, vnw.x, 1),
-          rsw = __shfl_down_sync(FULL, vsw.x, 1);
-    if (valid && lane == 0 && x4 != 0) {
-        le = p.X[D_E][i - 1];
-        lne = p.X[D_NE][i + P - 1];
-        lse = p.X[D_SE][i - P - 1];
-    }
-    if (valid && lane == 31) {  // x4+4 <= P: still inside the row pitch (or x=0 of the next row: unused)
-        rw = p.X[D_W][i + 4];
-        rnw = p.X[D_NW][i + P + 4];
-        rsw = p.X[D_SW][i - P + 4];
+    // element x4-1 of the east-moving populations, element x4+4 of the west-moving ones: from the neighbouring
+    // lane, except at the warp edges
+    {
+        const float se_ = __shfl_up_sync(FULL, ve.w, 1), sne_ = __shfl_up_sync(FULL, vne.w, 1),
+                    sse_ = __shfl_up_sync(FULL, vse.w, 1);
+        const float sw_ = __shfl_down_sync(FULL, vw.x, 1), snw_ = __shfl_down_sync(FULL, vnw.x, 1),
+                    ssw_ = __shfl_down_sync(FULL, vsw.x, 1);
+        if (!edge_l) {
+            le = se_;
+            lne = sne_;
+            lse = sse_;
+        }
+        if (!edge_r) {
+            rw = sw_;
+            rnw = snw_;
+            rsw = ssw_;
+        }
     }
     if (!valid) return;  // (lanes past the row end issued no cp.async)
+    if (LATE_CLS && flag != 0) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
 
     g[0][D_N] = vn.x; g[1][D_N] = vn.y; g[2][D_N] = vn.z; g[3][D_N] = vn.w;
     g[0][D_S] = vs.x; g[1][D_S] = vs.y; g[2][D_S] = vs.z; g[3][D_S] = vs.w;
@@ -308,6 +335,7 @@ cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, int block_
 {
     if (mode != MODE_FUSED) return launch_step_scalar(p, mode, mom, st);
     switch (dense_obstacles) {
+    case 3: return launch_vec4_flavour<3>(p, mom, block_rows, packed, index32, st);
     case 2: return launch_vec4_flavour<2>(p, mom, block_rows, packed, index32, st);
     case 1: return launch_vec4_flavour<1>(p, mom, block_rows, packed, index32, st);
     default: return launch_vec4_flavour<0>(p, mom, block_rows, packed, index32, st);
@@ -354,7 +382,8 @@ cudaError_t preload_step_kernels()
     cudaError_t e;
     if ((e = touch_vec4_flavour<0>()) != cudaSuccess) return e;
     if ((e = touch_vec4_flavour<1>()) != cudaSuccess) return e;
-    return touch_vec4_flavour<2>();
+    if ((e = touch_vec4_flavour<2>()) != cudaSuccess) return e;
+    return touch_vec4_flavour<3>();
 }
 #undef BLBM_TOUCH
 

@@ -152,7 +152,7 @@ def test_porous_channel_small(kernel, lazy):
 
 
 @pytest.mark.parametrize("lazy", [0, 1])
-@pytest.mark.parametrize("flavour", [1, 2])
+@pytest.mark.parametrize("flavour", [1, 2, 3])
 @pytest.mark.parametrize("rows", [1, 4, 16])
 @pytest.mark.parametrize("size", [(256, 128), (131, 23), (5, 4)])
 def test_staged_bounce_back_bit_exact(size, rows, lazy, flavour):
@@ -384,7 +384,7 @@ def _fuzz(lbm, ora, rng, w, h, tag, tunable, nops=120):
             lbm.set_lazy_barriers(int(rng.integers(0, 3)))
         elif op == 11:
             knob = int(rng.integers(0, 8))
-            val = {0: [1, 2, 4, 8, 16], 1: [4, 8], 2: [2, 3, 4], 3: [1, 2, 3], 4: [-1, 0, 1, 2], 5: [-1, 0, 1],
+            val = {0: [1, 2, 4, 8, 16], 1: [4, 8], 2: [2, 3, 4], 3: [1, 2, 3], 4: [-1, 0, 1, 2, 3], 5: [-1, 0, 1],
                    6: [0, 1], 7: [-1, 0, 1]}[knob]
             lbm.set_tuning(knob, int(rng.choice(val)))
         elif op == 12:
