@@ -331,9 +331,9 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
         // cells), unless overridden
         {
             const int flavour = h->vec4_dense < 0 ? (h->chain_active ? 2 : 0) : h->vec4_dense;
-            // 32-bit plane offsets pay off in the sparse flavour (64 instead of 72 registers: 2.91 vs 3.13 ms on the
-            // empty 16384^2 channel); the staged dense flavour is faster with 64-bit offsets (no spill: 3.09 vs 3.14)
-            const bool index32 = h->vec4_index32 < 0 ? flavour == 0 : h->vec4_index32 != 0;
+            // 32-bit plane offsets wherever the slab allows it (always on a B200 at the default block shape): one
+            // IMAD.WIDE per address, and the variants that then stay at 64 registers without a spill
+            const bool index32 = h->vec4_index32 != 0;
             e = launch_step_vec4(p, mode, mom, h->vec4_rows, flavour, h->vec4_packed != 0, index32, h->stream);
         }
         break;

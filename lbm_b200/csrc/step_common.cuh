@@ -9,6 +9,7 @@ namespace blbmk {
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void stg4(float *p, const float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+// (st.global.cs — the "streaming" hint — on these stores was measured: porous 3.12 vs 3.08 ms, channel no change.)
 
 // Offset of the cell population d is pulled from, for the cell at (x, device-row offset `i`).
 // Column W-1 follows the reference's flat indexing: i+1 is (0, y+1)  (SURVEY.md section 8 a-4).
