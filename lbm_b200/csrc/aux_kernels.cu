@@ -597,6 +597,13 @@ __global__ void __launch_bounds__(128) chain_replay_kernel(const uint32_t *idx, 
         b[d] = state[(size_t)(8 + d) * cap + e];
     }
     R = state[(size_t)16 * cap + e];
+    float ai[8], bi[8];  // as loaded: a chain that ends the call where it started is not written back
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        ai[d] = a[d];
+        bi[d] = b[d];
+    }
+    const float Ri = R;
     float m_x = 0.f, m_y = 0.f, r = 0.f;
     uint32_t left = nsteps;
     uint32_t par = parity0 & 1u;
@@ -622,12 +629,14 @@ __global__ void __launch_bounds__(128) chain_replay_kernel(const uint32_t *idx, 
         if (par == 0) collide_cell(a, R, omega, m_x, m_y, r);
         else collide_cell(b, R, omega, m_x, m_y, r);
     }
+    if (!same_bits17(a, b, R, ai, bi, Ri)) {
 #pragma unroll
-    for (int d = 0; d < 8; d++) {
-        state[(size_t)d * cap + e] = a[d];
-        state[(size_t)(8 + d) * cap + e] = b[d];
+        for (int d = 0; d < 8; d++) {
+            state[(size_t)d * cap + e] = a[d];
+            state[(size_t)(8 + d) * cap + e] = b[d];
+        }
+        state[(size_t)16 * cap + e] = R;
     }
-    state[(size_t)16 * cap + e] = R;
     const size_t i = idx[e];
     mx[i] = m_x;
     my[i] = m_y;

@@ -145,12 +145,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __host__ __device__ constexpr int stage_dir(int q) { return q == 0 ? D_NW : q == 1 ? D_N : q == 2 ? D_NE : q == 3 ? D_SW : q == 4 ? D_S : D_SE; }
 __host__ __device__ constexpr int stage_slot(int d) { return d == D_NW ? 0 : d == D_N ? 1 : d == D_NE ? 2 : d == D_SW ? 3 : d == D_S ? 4 : 5; }
 
+// The moment-storing variant (one launch per call) may use 85 registers instead of spilling at 64.
 // IDX: uint32_t plane offsets where a plane has fewer than 2^32 elements (every slab that fits a B200 at
 // rows-per-block 4), size_t otherwise.  The grid is (chunks along x, row blocks [, overflow of row blocks]) so that
 // no thread divides a linear block index.
 constexpr uint32_t GRID_Y = 32768;
 template <bool MOM, int V4_ROWS, int DENSE, bool PACKED, typename IDX>
-__global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? 1024 / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
+__global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
 {
     constexpr bool STAGED = DENSE >= 2;
     constexpr bool EAGER_CLS = DENSE == 3;  // class words read up front, without the chunk-flag test
