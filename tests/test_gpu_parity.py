@@ -151,6 +151,26 @@ def test_porous_channel_small(kernel, lazy):
     lbm.close()
 
 
+@pytest.mark.parametrize("flavour", [0, 2])
+def test_tall_lattice_uses_the_third_grid_dimension(flavour):
+    """More than 4 x 32768 rows: the vec4 kernel's row blocks spill over from gridDim.y into gridDim.z."""
+    w, h = 40, 140001
+    lbm = LBM(1.3, w, h, kernel=Kernel.Vec4, lazy_barriers=1 if flavour else 0)
+    lbm.set_tuning(4, flavour)
+    ora = Oracle(1.3, w, h)
+    rng = np.random.default_rng(5)
+    loc = np.unique(np.concatenate([rng.integers(w, w * (h - 1), size=4000),
+                                    np.arange(131070 * w + 3, 131075 * w + 3, w)]))  # across the y/z seam
+    pts = np.stack([loc, np.ones_like(loc)], 1).astype(np.uint64)
+    lbm.draw_points(pts)
+    ora.draw_points(pts.astype(np.uint32))
+    for n in (1, 6):
+        lbm.iterate(n)
+        ora.iterate(n)
+        compare_state(lbm, ora, f"tall {w}x{h} flavour {flavour} +{n}")
+    lbm.close()
+
+
 @pytest.mark.parametrize("lazy", [0, 1])
 @pytest.mark.parametrize("flavour", [1, 2, 3])
 @pytest.mark.parametrize("rows", [1, 4, 16])
