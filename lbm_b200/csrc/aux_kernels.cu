@@ -267,9 +267,54 @@ __global__ void summary_kernel(const float *__restrict__ mx, const float *__rest
     }
 }
 
+// curl.wgsl, four consecutive cells per thread with 128-bit accesses (a warp = one 128-cell chunk of a row, a block
+// = 8 rows); groups that touch column 0, column W-1 or the row end take the per-cell path of summary_kernel<0>.
+constexpr uint32_t CURL_ROWS = 8, CURL_GRID_Y = 32768;
+__global__ void __launch_bounds__(32 * CURL_ROWS) curl_vec4_kernel(const float *__restrict__ mx,
+                                                                   const float *__restrict__ my,
+                                                                   const float *__restrict__ rho,
+                                                                   float *__restrict__ out, const SlabGeom g)
+{
+    const uint32_t r = (blockIdx.z * CURL_GRID_Y + blockIdx.y) * CURL_ROWS + threadIdx.y;
+    const uint32_t x4 = (blockIdx.x * 32u + threadIdx.x) * 4u;
+    if (r >= g.rows || x4 >= g.W) return;
+    if (g.row0 + r >= g.Hg - 1) return;  // rows >= H-1 keep their old output
+    const size_t i = row_off(r, g.P) + x4;
+    if (x4 != 0 && x4 + 4 < g.W) {
+        const float4 m = *reinterpret_cast<const float4 *>(my + i);
+        const float4 up = *reinterpret_cast<const float4 *>(mx + i - g.P);
+        const float4 dn = *reinterpret_cast<const float4 *>(mx + i + g.P);
+        const float4 d = *reinterpret_cast<const float4 *>(rho + i);
+        const float l = my[i - 1], rgt = my[i + 4];
+        float4 o;
+        o.x = __fdiv_rn(__fmul_rn(10.0f, __fadd_rn(__fsub_rn(__fsub_rn(m.y, l), up.x), dn.x)), d.x);
+        o.y = __fdiv_rn(__fmul_rn(10.0f, __fadd_rn(__fsub_rn(__fsub_rn(m.z, m.x), up.y), dn.y)), d.y);
+        o.z = __fdiv_rn(__fmul_rn(10.0f, __fadd_rn(__fsub_rn(__fsub_rn(m.w, m.y), up.z), dn.z)), d.z);
+        o.w = __fdiv_rn(__fmul_rn(10.0f, __fadd_rn(__fsub_rn(__fsub_rn(rgt, m.z), up.w), dn.w)), d.w);
+        *reinterpret_cast<float4 *>(out + i) = o;
+        return;
+    }
+    for (uint32_t q = 0; q < 4; q++) {
+        const uint32_t x = x4 + q;
+        if (x == 0 || x >= g.W) continue;  // column 0 keeps its old output
+        const size_t j = i + q;
+        const float a = (x + 1 < g.W) ? my[j + 1] : my[j - x + g.P];  // flat index: (0, y+1) at column W-1
+        const float b = my[j - 1];
+        out[j] = __fdiv_rn(__fmul_rn(10.0f, __fadd_rn(__fsub_rn(__fsub_rn(a, b), mx[j - g.P]), mx[j + g.P])), rho[j]);
+    }
+}
+
 cudaError_t launch_summary(int stat, const float *mx, const float *my, const float *rho, float *out,
                            const SlabGeom &g, cudaStream_t st)
 {
+    if (stat == 0 && g.rows > 0 && g.W > 0) {
+        const uint32_t nbx = (g.W + 127u) / 128u, nrb = (g.rows + CURL_ROWS - 1) / CURL_ROWS;
+        dim3 grid(nbx, nrb < CURL_GRID_Y ? nrb : CURL_GRID_Y, (nrb + CURL_GRID_Y - 1) / CURL_GRID_Y), block(32, CURL_ROWS);
+        if (grid.z <= 65535u) {
+            curl_vec4_kernel<<<grid, block, 0, st>>>(mx, my, rho, out, g);
+            return cudaGetLastError();
+        }
+    }
     const size_t total = (size_t)g.rows * g.W;
     size_t nb = (total + 255) / 256;
     if (nb > 148 * 16) nb = 148 * 16;
@@ -740,6 +785,7 @@ cudaError_t preload_aux_kernels()
     BLBM_TOUCH(build_class_kernel<false>);
     BLBM_TOUCH(build_class_kernel<true>);
     BLBM_TOUCH(precollision_moments_kernel);
+    BLBM_TOUCH(curl_vec4_kernel);
     BLBM_TOUCH(summary_kernel<0>);
     BLBM_TOUCH(summary_kernel<1>);
     BLBM_TOUCH(summary_kernel<2>);
