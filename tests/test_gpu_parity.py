@@ -151,6 +151,27 @@ def test_porous_channel_small(kernel, lazy):
     lbm.close()
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("size", [(70001, 5), (65536, 4)])
+def test_wide_lattice(kernel, size):
+    """Rows wider than 2^16 cells (BASELINE.json configs[4] has W = 65536), ragged and not: chunk indexing, the
+    flat-index wrap at column W-1, paints in the last chunk."""
+    w, h = size
+    lbm = LBM(1.1, w, h, kernel=kernel, lazy_barriers=1)
+    ora = Oracle(1.1, w, h)
+    rng = np.random.default_rng(w)
+    loc = np.unique(np.concatenate([rng.integers(w, w * (h - 1), size=3000),
+                                    np.array([2 * w - 1, 2 * w - 2, 2 * w - 130, 3 * w - 1, w + 1, 2 * w + 65535])]))
+    pts = np.stack([loc, np.ones_like(loc)], 1).astype(np.uint32)
+    lbm.draw_points(pts)
+    ora.draw_points(pts)
+    for n in (1, 9):
+        lbm.iterate(n)
+        ora.iterate(n)
+        compare_state(lbm, ora, f"wide {w}x{h} {kernel.name} +{n}")
+    lbm.close()
+
+
 @pytest.mark.parametrize("flavour", [0, 2])
 def test_tall_lattice_uses_the_third_grid_dimension(flavour):
     """More than 4 x 32768 rows: the vec4 kernel's row blocks spill over from gridDim.y into gridDim.z."""
@@ -322,6 +343,33 @@ def test_full_size_properties_16384_porous():
     for other in ("dense", "tma"):
         for a, b, what in zip(res["chain"], res[other], ("curl", "rho", "n", "rest", "sw")):
             assert_same_bits(a, b, f"chain vs {other}: {what} at 16384^2")
+
+
+def test_full_size_32768_offset_widths_agree():
+    """BASELINE.json configs[3] at full size on one GPU (32768^2 = 1.07 G cells, 89 GiB resident, far beyond the
+    oracle): plane offsets pass 2^30 elements and 2^32 bytes.  The vec4 kernel with 32-bit plane offsets (default)
+    and with 64-bit offsets must agree bit for bit on curl and density after the same steps; the inlet column
+    must not move and the far corner must have been updated."""
+    w = h = 32768
+    cyl = disc_pairs(w, w // 4, h // 2, 256).astype(np.uint64)
+    res = []
+    for index32 in (1, 0):
+        lbm = LBM(omega_from_viscosity(0.0512), w, h, kernel=Kernel.Vec4)
+        lbm.set_tuning(7, index32)
+        lbm.draw_points(cyl)
+        lbm.iterate(7)
+        out, rho = lbm.read_output(), lbm.read_moments()[2]
+        assert np.isfinite(rho).all() and rho[h - 2, w - 1] > 0.5
+        e = lbm.read_population(5)
+        assert (e[1:h - 1, 0] == e[1, 0]).all()  # inlet column: still the uniform equilibrium
+        del e
+        res.append((out, rho))
+        lbm.close()
+    assert_same_bits(res[0][0], res[1][0], "curl, 32- vs 64-bit offsets at 32768^2")
+    assert_same_bits(res[0][1], res[1][1], "rho, 32- vs 64-bit offsets at 32768^2")
+    # the wake has started to form behind the cylinder and nowhere else
+    assert np.abs(res[0][0][h // 2 - 300:h // 2 + 300, w // 4 - 300:w // 4 + 300]).max() > 0
+    assert np.abs(res[0][0][16:200, w // 2:w - 64]).max() == 0
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
