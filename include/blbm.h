@@ -230,7 +230,8 @@ typedef enum blbm_tune {
     BLBM_TUNE_TMA_CTAS_PER_SM = 3, /* persistent CTAs per SM: 1..8 (default 2) */
     BLBM_TUNE_VEC4_DENSE = 4,      /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles,
                                       2 dense + own-row vectors staged in shared memory with cp.async (what auto
-                                      picks wherever the barrier-chain table is active) */
+                                      picks wherever the barrier-chain table is active), 3 as 2 with the class
+                                      words read without the chunk-flag test */
     BLBM_TUNE_CUDA_GRAPHS = 5,     /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
     BLBM_TUNE_VEC4_PACKED = 6,     /* collide cell pairs with packed fp32 adds (sm_100 FADD2): 0 (default) or 1; same bits,
                                       measured slower (register pressure) */

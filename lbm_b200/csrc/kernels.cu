@@ -122,19 +122,23 @@ cudaError_t launch_step_scalar(const StepParams &p, int mode, bool mom, cudaStre
 // ------------------------------------------------------------------------------------------------
 // vec4 kernel: four consecutive cells per thread, every global access an aligned 128-bit transaction.
 // The six populations that move in x are realigned by one float through warp shuffles; the lane at
-// the warp edge fetches the single missing float itself.  A block is 32 x 8 threads = 128 x 8 cells.
-// Cells that need anything but a plain pull (class word != 0, column W-1, ragged row end) take a
-// per-cell fix-up path after the vector loads.
+// the warp edge fetches the single missing float itself.  A block is 32 x V4_ROWS threads = 128 x V4_ROWS
+// cells (V4_ROWS = 4 by default; 1, 2, 8, 16 through blbm_set_tuning).  Cells that need anything but a plain
+// pull (class word != 0, column W-1, ragged row end) take a per-cell fix-up path after the vector loads.
+//
+// DENSE selects the flavour of the bounce-back fix-up (same results in every flavour):
+//   0  sparse: one branch per direction, and the class words are read only after the pulls have arrived, inside
+//      a warp-uniform branch on the chunk flag (best where obstacles are rare: the clean path is 64 registers,
+//      no spill; empty 16384^2 channel 2.89 ms);
+//   1  dense: branch-free selects over the directions (every direction is needed by some lane anyway);
+//   2  dense + staged (what the handle picks wherever the barrier-chain table is active): the six own-row vectors
+//      the bounce-back needs (the cell's own n, s, ne, nw, se, sw) are fetched into shared memory with cp.async
+//      together with the pulls, so they cost no registers while in flight and the fix-up no longer pays a second,
+//      dependent round trip to L2 after the class words arrive (porous 16384^2: 3.41 -> 3.26 ms);
+//   3  as 2, with the class words read up front without consulting the chunk flag (+2 B/cell in clean chunks;
+//      within 0.3 % of flavour 2 on a fully porous lattice).
+// PACKED collides cell pairs with Blackwell's packed fp32 adds (FADD2): same bits, measured slower (registers).
 // ------------------------------------------------------------------------------------------------
-// rows per block is a tuning knob (blbm_set_tuning): 1, 2, 4 (default), 8 or 16
-// DENSE selects the flavour of the bounce-back fix-up: branch-free over the directions (best where obstacles
-// are dense, e.g. porous media: +2.5 %) or one branch per direction (best where they are sparse: the clean
-// path then compiles to 64 registers without any spill, +5 % on an empty channel).  Same results either way.
-// DENSE == 2 additionally stages the six own-row vectors the bounce-back needs (the cell's own n, s, ne, nw, se,
-// sw) in shared memory with cp.async, issued together with the pull loads: they cost no registers while in
-// flight, and the fix-up no longer waits for a second, dependent round trip to L2 after the class words arrive.
-// (Reading the class words without the chunk-flag test in front was measured too: slower, 3.46 vs 3.25 ms.)
-// PACKED collides cell pairs with Blackwell's packed fp32 adds (FADD2): same bits, a quarter fewer instructions.
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
