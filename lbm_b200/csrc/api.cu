@@ -518,6 +518,13 @@ int rebuild_class(blbm *h, uint32_t lo, uint32_t hi, bool big_change)
 
 int fill_equilibrium(blbm *h, float ux, int single_index)
 {
+    // Leave the chain table first: the flush also clears CLS_CHAIN in both class planes.  (Dropping the table
+    // with the bits still set made the next collide half-step keep stale moments at barrier cells, and a step
+    // kernel with the table switched off treat their plane slots as don't-care.)
+    {
+        const int rcf = chain_flush(h);
+        if (rcf) return rcf;
+    }
     // set_equil on the host in fp32 with the reference's op order (lbm.rs:611-643); uy = 0, rho = 1
     float v9[9];
     {
@@ -602,7 +609,6 @@ int fill_equilibrium(blbm *h, float ux, int single_index)
     h->step = 0;
     h->frame = 0;
     h->regimeT = false;
-    h->chain_active = false;  // the table described the old populations
     consume_pending_class(h);
     h->halo_dirty = false;  // every slab filled its halo rows with the same constants
     return BLBM_OK;
