@@ -98,3 +98,14 @@ def test_packed_adds_are_never_contracted_into_packed_fmas():
     sass = subprocess.run([cuobjdump, "-sass", lbm_b200.library_path()], capture_output=True, text=True).stdout
     assert "FADD2" in sass
     assert "FFMA2" not in sass and "FMUL2" not in sass
+
+
+def test_rust_sys_crate_declares_every_entry_point():
+    """rust/blbm-sys is shipped as source only (no Rust toolchain in this image): at least keep it complete —
+    one `pub fn` per symbol of include/blbm.h — and its tuning constants in step with the header's enum."""
+    rs = open(os.path.join(ROOT, "rust", "blbm-sys", "src", "lib.rs")).read()
+    missing = [s for s in declared_symbols() if not re.search(r"\bfn\s+" + s + r"\b", rs)]
+    assert not missing, missing
+    hdr = open(os.path.join(ROOT, "include", "blbm.h")).read()
+    for name, val in re.findall(r"\b(BLBM_TUNE_[A-Z0-9_]+)\s*=\s*(\d+)", hdr):
+        assert re.search(r"\b" + name + r":\s*c_int\s*=\s*" + val + r"\b", rs), f"{name} = {val} missing in blbm-sys"
