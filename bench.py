@@ -193,9 +193,12 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "MLUPS (D2Q9 fp32)", "value": val, "unit": "MLUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "W": w, "H_per_gpu": rows_gpu, "omega": omega, "u0": u0,
-                   "mask": kind},
+        "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "W": w, "H": rows_gpu if args.workload in STRONG else rows_gpu * args.gpus,
+                   "H_per_gpu": rows_gpu // args.gpus if args.workload in STRONG else rows_gpu, "omega": omega,
+                   "u0": u0, "mask": kind, "kernel": "cpu oracle (8 passes per step)",
+                   "parallelism": f"{threads()} host threads"},
         "cpu_baseline": {"value": val, "unit": "MLUPS", "cores": threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -213,7 +216,7 @@ def main():
     ap.add_argument("--block-rows", type=int, default=0, help="vec4 kernel rows per block (4, 8, 16); 0 = default")
     ap.add_argument("--graphs", type=int, default=-1, help="CUDA graphs for the step loop: -1 auto, 0 off, 1 on")
     ap.add_argument("--dense", type=int, default=-1, help="vec4 bounce flavour: -1 auto, 0 sparse, 1 dense, 2 dense + cp.async staging")
-    ap.add_argument("--packed", type=int, default=-1, help="vec4 packed fp32 adds (FADD2): -1 default (on), 0, 1")
+    ap.add_argument("--packed", type=int, default=-1, help="vec4 packed fp32 adds (FADD2): -1 default (off: measured slower), 0, 1")
     ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 auto, 0, 1")
     ap.add_argument("--tma-rows", type=int, default=0)
     ap.add_argument("--tma-stages", type=int, default=0)

@@ -109,3 +109,34 @@ def test_rust_sys_crate_declares_every_entry_point():
     hdr = open(os.path.join(ROOT, "include", "blbm.h")).read()
     for name, val in re.findall(r"\b(BLBM_TUNE_[A-Z0-9_]+)\s*=\s*(\d+)", hdr):
         assert re.search(r"\b" + name + r":\s*c_int\s*=\s*" + val + r"\b", rs), f"{name} = {val} missing in blbm-sys"
+
+
+def test_default_step_kernels_keep_their_register_budget_and_wide_accesses():
+    """Static guard for the measured configuration (no GPU needed): the instantiations the default launch paths
+    use — step_vec4_kernel<no moments, 4 rows, flavour 0 | 2, scalar adds, 32-bit offsets> — must stay at
+    64 registers without a spill (8 blocks of 128 threads per SM), move the populations with 128-bit global
+    accesses, stage the bounce-back's own rows with cp.async (flavour 2), realign the x+-1 gathers with warp
+    shuffles; the TMA variant must really issue TMA loads behind mbarrier waits.  profiles/r1/sass_summary.txt
+    is the same table for every kernel of the library."""
+    import importlib.util
+    import shutil
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    spec = importlib.util.spec_from_file_location("sass_summary", os.path.join(ROOT, "profiles", "sass_summary.py"))
+    ss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ss)
+    res = ss.resource_usage()
+    counts, _ = ss.sass_counts()
+    names = {ss.short(v): k for k, v in ss.demangle(sorted(res)).items()}
+    for flavour in (0, 2):
+        k = names[f"step_vec4_kernel<(bool)0, (int)4, (int){flavour}, (bool)0, u32>"]
+        assert int(res[k]["REG"]) <= 64 and int(res[k]["STACK"]) == 0, (flavour, res[k])
+        c = counts[k]
+        assert c["LDG.E.128"] >= 9 and c["STG.E.128"] >= 9 and c["SHFL"] >= 6 and not c["LDL"] and not c["STL"]
+        assert (c["LDGSTS"] > 0) == (flavour == 2)
+    # the moment-storing launch (one per iterate) may use more registers but must not spill either
+    for flavour in (0, 2):
+        k = names[f"step_vec4_kernel<(bool)1, (int)4, (int){flavour}, (bool)0, u32>"]
+        assert int(res[k]["REG"]) <= 80 and int(res[k]["STACK"]) == 0
+    tma = [k for n, k in names.items() if n.startswith("step_tma_kernel<")]
+    assert tma and all(counts[k]["UTMALDG"] >= 9 and counts[k]["SYNCS"] > 0 and int(res[k]["STACK"]) == 0 for k in tma)
