@@ -1,0 +1,355 @@
+"""TEST INFRASTRUCTURE — a SIMT executor for the reference's WGSL compute shaders: the same parser and the same
+semantics as oracle/wgsl_interp.py, but all invocations of a dispatch are evaluated together on numpy arrays
+under an execution mask, the way a GPU runs them.  That makes the reference's shader text executable at the
+reference's own problem size: BASELINE.json configs[0] (512 x 256, 10,000 steps = 80,000 dispatches of 131,072
+invocations) takes minutes instead of days, so the 10k-step parity target of the north star is pinned to the
+reference's source and not to a restatement (tests/golden/make_wgsl_config1.py, tests/test_wgsl_pin.py).
+
+Why evaluating a dispatch "all lanes at once" is the same as any sequential or parallel order: the executor
+REFUSES a shader unless, within one dispatch, every store goes to the invocation's own element (index ==
+global_invocation_id.x) and every load from an array that the dispatch also stores to reads the invocation's own
+element (`_check_own`).  Then no invocation can observe another one's stores and the result does not depend on
+scheduling.  All step / summary shaders of the reference have that property; the scatter of barrier_draw.wgsl and
+the vec3 colour maps stay with the scalar interpreter.
+
+Semantics (identical to wgsl_interp.py and to the oracle's normative block): every fp32
+operation individually rounded (numpy float32 element-wise arithmetic; IEEE division and sqrt), u32 arithmetic
+wraps, out-of-range reads return 0, out-of-range writes are dropped, abstract literal expressions are evaluated in
+f64 / integers and take the concrete type of the operand they meet.
+
+Only tests/ and the golden generators may import this; the product never does.
+"""
+import os
+
+import numpy as np
+
+from .wgsl_interp import NW, N, NE, W, REST, E, SW, S, SE, Parser, Shader, WgslLBM, _is_abstract, f32, i32, u32  # noqa: F401
+
+_CONCRETE = {"u32": u32, "i32": i32, "f32": f32}
+
+
+def _concretise(v, like):
+    if isinstance(like, np.ndarray):
+        return like.dtype.type(v)
+    return type(like)(v)
+
+
+def _unify(a, b):
+    if _is_abstract(a) and not _is_abstract(b):
+        a = _concretise(a, b)
+    elif _is_abstract(b) and not _is_abstract(a):
+        b = _concretise(b, a)
+    elif _is_abstract(a) and _is_abstract(b):
+        if isinstance(a, float) or isinstance(b, float):
+            a, b = float(a), float(b)
+    return a, b
+
+
+def _is_int(v):
+    if isinstance(v, np.ndarray):
+        return v.dtype.kind in "iu"
+    return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
+
+
+class _Frame:
+    """one function activation: lexical scopes, the lanes still running, the return value being assembled"""
+
+    def __init__(self, scopes, active):
+        self.scopes = scopes
+        self.active = active
+        self.ret = None
+
+
+class VecShader:
+    def __init__(self, path):
+        self.path = path
+        self.structs, self.globals, self.funcs = Parser(open(path).read()).module()
+        if "main" not in self.funcs or "compute" not in self.funcs["main"]["attrs"]:
+            raise SyntaxError("WGSL: no @compute fn main")
+        self.workgroup_size = int(self.funcs["main"]["attrs"]["workgroup_size"][0])
+
+    # bindings as for Shader.dispatch: {(group, binding): numpy array | numpy scalar | dict (uniform struct)}
+    def dispatch(self, workgroups, bindings):
+        n = workgroups * self.workgroup_size
+        self.n = n
+        self.gid = np.arange(n, dtype=u32)
+        self.arrays = {}
+        self.stored = set()
+        env = {}
+        for name, g in self.globals.items():
+            key = (g["group"], g["binding"])
+            if key not in bindings:
+                raise KeyError(f"WGSL: nothing bound at @group({key[0]}) @binding({key[1]}) for `{name}`")
+            b = bindings[key]
+            if (g["type"][0] == "array") != isinstance(b, np.ndarray):
+                raise TypeError(f"WGSL: binding for `{name}` has the wrong shape")
+            if isinstance(b, np.ndarray):
+                if b.dtype.names:
+                    raise NotImplementedError("SIMT executor: arrays of structs")
+                self.arrays[name] = b
+                env[name] = ("array", name)
+            else:
+                env[name] = b
+        fn = self.funcs["main"]
+        scope = {}
+        for pname, _, pattrs in fn["params"]:
+            if pattrs.get("builtin") == ["global_invocation_id"]:
+                scope[pname] = {"x": self.gid, "y": u32(0), "z": u32(0)}
+            else:
+                raise NotImplementedError(f"WGSL: builtin {pattrs}")
+        self.env = env
+        with np.errstate(all="ignore"):
+            frame = _Frame([env, scope], np.ones(n, dtype=bool))
+            self._block(fn["body"], frame)
+
+    # -- statements ------------------------------------------------------------------------------------------
+    def _block(self, stmts, fr):
+        fr.scopes.append({})
+        for s in stmts:
+            if not fr.active.any():
+                break
+            self._stmt(s, fr)
+        fr.scopes.pop()
+
+    def _stmt(self, s, fr):
+        kind = s[0]
+        if kind == "return":
+            if s[1] is not None:
+                v = self._eval(s[1], fr)
+                if fr.ret is None:
+                    fr.ret = v if not isinstance(v, np.ndarray) else v.copy()
+                else:
+                    fr.ret = np.where(fr.active, v, fr.ret)
+            fr.active = np.zeros_like(fr.active)
+        elif kind == "block":
+            self._block(s[1], fr)
+        elif kind == "if":
+            cond = self._eval(s[1], fr)
+            if not isinstance(cond, np.ndarray):
+                cond = np.full(self.n, bool(cond))
+            before = fr.active
+            taken, not_taken = before & cond, before & ~cond
+            after = np.zeros_like(before)
+            if taken.any():
+                fr.active = taken
+                self._block(s[2], fr)
+                after |= fr.active
+            if s[3] is not None and not_taken.any():
+                fr.active = not_taken
+                self._block(s[3], fr)
+                after |= fr.active
+            elif s[3] is None:
+                after |= not_taken
+            fr.active = after
+        elif kind in ("let", "var"):
+            if kind == "var":
+                raise NotImplementedError("SIMT executor: function-scope `var` (none of the step shaders has one)")
+            v = self._eval(s[3], fr)
+            if _is_abstract(v):
+                v = f32(v) if isinstance(v, float) else i32(v)
+            fr.scopes[-1][s[1]] = v
+        elif kind == "assign":
+            op, lhs, rhs = s[1], s[2], s[3]
+            val = self._eval(rhs, fr)
+            if op != "=":
+                val = self._binop(op[0], self._eval(lhs, fr), val)
+            if lhs[0] != "index":
+                raise NotImplementedError("SIMT executor: assignment to a local")
+            arr = self._eval(lhs[1], fr)
+            idx = self._eval(lhs[2], fr)
+            self._store(arr[1], idx, val, fr.active)
+        elif kind == "expr":
+            self._eval(s[1], fr)
+        else:
+            raise NotImplementedError(f"SIMT executor: statement `{kind}`")
+
+    # -- memory ----------------------------------------------------------------------------------------------
+    def _check_own(self, name, idx, active, what):
+        if idx is self.gid:
+            return
+        if not (isinstance(idx, np.ndarray) and np.array_equal(idx[active], self.gid[active])):
+            raise RuntimeError(f"SIMT executor: {what} `{name}` at another invocation's element in "
+                               f"{os.path.basename(self.path)}: result would depend on scheduling")
+
+    def _load(self, name, idx, active):
+        data = self.arrays[name]
+        if name in self.stored:
+            self._check_own(name, idx, active, "load from stored-to array")
+        m = len(data)
+        if idx is self.gid:
+            if m >= self.n:
+                return data[:self.n].copy()
+            out = np.zeros(self.n, dtype=data.dtype)
+            out[:m] = data
+            return out
+        if not isinstance(idx, np.ndarray):
+            i = int(idx)
+            return data[i] if 0 <= i < m else data.dtype.type(0)
+        idx64 = idx.astype(np.int64)
+        ok = (idx64 >= 0) & (idx64 < m)
+        out = data[np.where(ok, idx64, 0)]
+        out[~ok] = 0
+        return out
+
+    def _store(self, name, idx, val, active):
+        data = self.arrays[name]
+        self._check_own(name, idx, active, "store to")
+        self.stored.add(name)
+        m = min(len(data), self.n)
+        if _is_abstract(val):
+            val = data.dtype.type(val)
+        if isinstance(val, np.ndarray):
+            if val.dtype != data.dtype:
+                raise TypeError(f"WGSL: storing {val.dtype} into array<{data.dtype}> `{name}`")
+            np.copyto(data[:m], val[:m], where=active[:m])
+        else:
+            if np.dtype(type(val)) != data.dtype:
+                raise TypeError(f"WGSL: storing {type(val)} into array<{data.dtype}> `{name}`")
+            data[:m][active[:m]] = val
+
+    # -- expressions -----------------------------------------------------------------------------------------
+    def _lookup(self, name, fr):
+        for sc in reversed(fr.scopes):
+            if name in sc:
+                return sc[name]
+        raise NameError(f"WGSL: undefined `{name}`")
+
+    def _eval(self, e, fr):
+        kind = e[0]
+        if kind == "lit":
+            return _CONCRETE.get(e[2], lambda x: x)(e[1])
+        if kind == "var":
+            return self._lookup(e[1], fr)
+        if kind == "member":
+            base = self._eval(e[1], fr)
+            if isinstance(base, dict):
+                return base[e[2]]
+            raise TypeError(f"WGSL: member .{e[2]} of {type(base)}")
+        if kind == "index":
+            arr = self._eval(e[1], fr)
+            if not (isinstance(arr, tuple) and arr[0] == "array"):
+                raise TypeError("WGSL: indexing a non-array")
+            return self._load(arr[1], self._eval(e[2], fr), fr.active)
+        if kind == "neg":
+            return -self._eval(e[1], fr)
+        if kind == "not":
+            return np.logical_not(self._eval(e[1], fr))
+        if kind == "bin":
+            op = e[1]
+            a, b = self._eval(e[2], fr), self._eval(e[3], fr)  # no side effects in expressions: no short circuit needed
+            if op == "&&":
+                return np.logical_and(a, b)
+            if op == "||":
+                return np.logical_or(a, b)
+            return self._binop(op, a, b)
+        if kind == "call":
+            return self._call(e[1], [self._eval(a, fr) for a in e[2]], fr)
+        raise NotImplementedError(kind)
+
+    @staticmethod
+    def _binop(op, a, b):
+        a, b = _unify(a, b)
+        if not _is_abstract(a):
+            ta = a.dtype if isinstance(a, np.ndarray) else np.dtype(type(a))
+            tb = b.dtype if isinstance(b, np.ndarray) else np.dtype(type(b))
+            if ta != tb:
+                raise TypeError(f"WGSL: operands of `{op}` have types {ta} and {tb}")
+        if op == "+":
+            return a + b
+        if op == "-":
+            return a - b
+        if op == "*":
+            return a * b
+        if op == "/":
+            if _is_int(a):
+                if _is_abstract(a):
+                    return a if b == 0 else a // b
+                zero = b == 0
+                q = np.floor_divide(a, np.where(zero, 1, b).astype(np.asarray(a).dtype))
+                return np.where(zero, a, q).astype(np.asarray(a).dtype) if np.ndim(q) else (a if zero else q)
+            return a / b
+        if op == "%":
+            if _is_int(a):
+                if _is_abstract(a):
+                    return 0 if b == 0 else a % b
+                zero = b == 0
+                r = np.remainder(a, np.where(zero, 1, b).astype(np.asarray(a).dtype))
+                return np.where(zero, 0, r).astype(np.asarray(a).dtype) if np.ndim(r) else (type(a)(0) if zero else r)
+            return np.fmod(a, b)
+        if op == "==":
+            return a == b
+        if op == "!=":
+            return a != b
+        if op == "<":
+            return a < b
+        if op == ">":
+            return a > b
+        if op == "<=":
+            return a <= b
+        if op == ">=":
+            return a >= b
+        raise NotImplementedError(op)
+
+    def _call(self, name, args, fr):
+        if name in self.funcs:
+            fn = self.funcs[name]
+            scope = {}
+            for (pname, pty, _), a in zip(fn["params"], args):
+                if _is_abstract(a):
+                    a = _CONCRETE[pty[0]](a)
+                scope[pname] = a
+            inner = _Frame([self.env, scope], fr.active.copy())
+            self._block(fn["body"], inner)
+            return inner.ret
+        if name == "f32":
+            a = args[0]
+            return a.astype(f32) if isinstance(a, np.ndarray) else f32(a)
+        if name == "u32":
+            a = args[0]
+            return a.astype(u32) if isinstance(a, np.ndarray) else u32(int(a) & 0xffffffff)
+        if name == "sqrt":
+            a = args[0]
+            return np.sqrt(f32(a)) if _is_abstract(a) else np.sqrt(a)
+        if name == "floor":
+            a = args[0]
+            return np.floor(f32(a)) if _is_abstract(a) else np.floor(a)
+        if name == "abs":
+            return np.abs(args[0])
+        if name in ("min", "max"):
+            a, b = _unify(args[0], args[1])
+            return (np.minimum if name == "min" else np.maximum)(a, b)
+        if name == "clamp":
+            x, lo, hi = args
+            if _is_abstract(lo):
+                lo = _concretise(lo, x)
+            if _is_abstract(hi):
+                hi = _concretise(hi, x)
+            return np.minimum(np.maximum(x, lo), hi)  # WGSL: clamp(e, low, high) = min(max(e, low), high)
+        raise NotImplementedError(f"SIMT executor: function `{name}`")
+
+
+class WgslLBMVec(WgslLBM):
+    """WgslLBM (the reference's host-side dispatch order, lbm.rs) with the step and summary shaders executed by the
+    SIMT executor; barrier_draw.wgsl (a scatter) and the vec3 colour maps keep the scalar interpreter."""
+
+    VECTOR = ("pre_corner", "pre_cardinal", "col_cardinal", "col_corner", "ne_sw", "nw_se", "n_s", "e_w",
+              "ux", "uy", "rho", "speed", "curl")
+
+    def __init__(self, omega, x, y, inflow_ux=0.1, root=None):
+        from . import wgsl_interp
+        root = root or wgsl_interp.SHADER_ROOT
+        super().__init__(omega, x, y, inflow_ux=inflow_ux, root=root)
+        rel = {"pre_corner": "pre_collision/corner_pre_collision.wgsl",
+               "pre_cardinal": "pre_collision/cardinal_pre_collision.wgsl",
+               "col_cardinal": "collision/cardinal_collision.wgsl", "col_corner": "collision/corner_collision.wgsl",
+               "ne_sw": "stream/ne_sw_stream.wgsl", "nw_se": "stream/se_nw_stream.wgsl",
+               "n_s": "stream/n_s_stream.wgsl", "e_w": "stream/e_w_stream.wgsl", "ux": "summary_stats/ux.wgsl",
+               "uy": "summary_stats/uy.wgsl", "rho": "summary_stats/rho.wgsl", "speed": "summary_stats/speed.wgsl",
+               "curl": "summary_stats/curl.wgsl"}
+        self.vsh = {k: VecShader(os.path.join(root, v)) for k, v in rel.items()}
+
+    def _run(self, name, bindings):
+        if name in self.vsh:
+            self.vsh[name].dispatch(self.work_groups, bindings)
+        else:
+            self.sh[name].dispatch(self.work_groups, bindings)

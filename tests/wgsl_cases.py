@@ -73,3 +73,57 @@ def replay(script, sim, snapshot):
         else:
             getattr(sim, name)()
     return shots
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Larger lattices, executed from the reference's WGSL text by the SIMT executor (oracle/wgsl_simt.py) and stored as
+# sha256 digests per buffer (tests/golden/wgsl_wide.npz, tests/golden/make_wgsl_wide.py): sizes at which the CUDA
+# kernels' structure is exercised — many 128-cell chunks per row, many row blocks, ragged row lengths, rows wider
+# than 4096 cells, the barrier-chain table with paints and erases while a stream is pending.
+def _porous_wide(w, h):
+    disc = disc_pairs(w, w // 3, h // 2, 9)
+    return [("draw", porous_pairs(w, h).astype(np.uint32)), ("iterate", 1), ("compare",), ("iterate", 60),
+            ("compare",), ("draw", disc.astype(np.uint32)), ("iterate", 40), ("compare",),
+            ("draw", disc_pairs(w, w // 3, h // 2, 9, val=0).astype(np.uint32)), ("omega", 1.2), ("iterate", 20),
+            ("compare",), ("summary", 4), ("compare",), ("summary", 3), ("compare",)]
+
+
+def _box(w, h, steps=(1, 99, 200)):
+    ys = np.arange(h, dtype=np.uint64)
+    loc = np.concatenate([ys * np.uint64(w) + np.uint64(1), ys * np.uint64(w) + np.uint64(w - 1)])
+    return [("draw", np.stack([loc, np.ones_like(loc)], 1).astype(np.uint32)), ("iterate", steps[0]), ("compare",),
+            ("iterate", steps[1]), ("compare",), ("iterate", steps[2]), ("compare",), ("summary", 1), ("compare",)]
+
+
+def _porous_strip(w, h):
+    return [("draw", porous_pairs(w, h).astype(np.uint32)), ("iterate", 1), ("compare",), ("iterate", 39),
+            ("compare",)]
+
+
+def wide_cases():
+    out = {}
+    out["porous_1024x512"] = (1.0, 1024, 512, 0.05, _porous_wide(1024, 512))
+    out["box_512x512"] = (1.25, 512, 512, 0.1, _box(512, 512))
+    # BASELINE.json configs[1] at FULL SIZE (4096^2 closed box) and a 256-row strip of
+    # configs[2] at its full row length (16384 cells, 15 % porous)
+    out["box_4096x4096"] = (1.25, 4096, 4096, 0.1, _box(4096, 4096, steps=(1, 19, 40)))
+    out["porous_16384x256"] = (1.0, 16384, 256, 0.05, _porous_strip(16384, 256))
+    for w, h, steps in ((300, 170, 40), (1001, 37, 30), (4100, 5, 12)):
+        rng = np.random.default_rng(9000 * w + h)
+        out[f"random_{w}x{h}"] = (1.0 / (3 * 0.02 + 0.5), w, h, 0.1, random_script(rng, w, h, max_steps=steps))
+    return out
+
+
+def digest_snapshot(st):
+    """sha256 per buffer of a snapshot dict (NaN payloads canonicalised: they are not part of the contract)"""
+    import hashlib
+    out = {}
+    for k in STATE_KEYS:
+        a = np.ascontiguousarray(st[k])
+        if a.dtype == np.float32:
+            a = a.copy()
+            a[np.isnan(a)] = np.float32(np.nan)
+        elif k == "barrier":
+            a = a.astype(np.uint32)
+        out[k] = hashlib.sha256(a.tobytes()).hexdigest()
+    return out
