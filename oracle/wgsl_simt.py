@@ -7,10 +7,12 @@ reference's source and not to a restatement (tests/golden/make_wgsl_config1.py, 
 
 Why evaluating a dispatch "all lanes at once" is the same as any sequential or parallel order: the executor
 REFUSES a shader unless, within one dispatch, every store goes to the invocation's own element (index ==
-global_invocation_id.x) and every load from an array that the dispatch also stores to reads the invocation's own
-element (`_check_own`).  Then no invocation can observe another one's stores and the result does not depend on
-scheduling.  All step / summary shaders of the reference have that property; the scatter of barrier_draw.wgsl and
-the vec3 colour maps stay with the scalar interpreter.
+global_invocation_id.x) and every load from an array that the dispatch also stores to — before or after the load
+in program order — reads the invocation's own element (`_check_own`, `_Dispatch.stored / foreign`).  Then no
+invocation can observe another one's stores and the result does not depend on scheduling; for the same reason
+the invocations may be split into contiguous chunks that run on several host threads (`threads=`; numpy releases
+the GIL inside array operations).  All step / summary shaders of the reference have that property; the scatter of
+barrier_draw.wgsl and the vec3 colour maps stay with the scalar interpreter.
 
 Semantics (identical to wgsl_interp.py and to the oracle's normative block): every fp32
 operation individually rounded (numpy float32 element-wise arithmetic; IEEE division and sqrt), u32 arithmetic
@@ -20,6 +22,7 @@ f64 / integers and take the concrete type of the operand they meet.
 Only tests/ and the golden generators may import this; the product never does.
 """
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -60,6 +63,20 @@ class _Frame:
         self.ret = None
 
 
+class _Dispatch:
+    """what the chunks of one dispatch share: the bound arrays and the record of which arrays were stored to and
+    which were read at another invocation's element (set operations are atomic under the GIL; every access first
+    records itself and then looks at the other set, so of two conflicting accesses at least one sees the other)"""
+
+    def __init__(self, arrays, env, path):
+        self.arrays, self.env, self.path = arrays, env, path
+        self.stored, self.foreign = set(), set()
+
+    def conflict(self, name):
+        return RuntimeError(f"SIMT executor: `{name}` is stored to and also read or written at another invocation's "
+                            f"element in {os.path.basename(self.path)}: the result would depend on scheduling")
+
+
 class VecShader:
     def __init__(self, path):
         self.path = path
@@ -69,13 +86,9 @@ class VecShader:
         self.workgroup_size = int(self.funcs["main"]["attrs"]["workgroup_size"][0])
 
     # bindings as for Shader.dispatch: {(group, binding): numpy array | numpy scalar | dict (uniform struct)}
-    def dispatch(self, workgroups, bindings):
+    def dispatch(self, workgroups, bindings, threads=1, pool=None):
         n = workgroups * self.workgroup_size
-        self.n = n
-        self.gid = np.arange(n, dtype=u32)
-        self.arrays = {}
-        self.stored = set()
-        env = {}
+        arrays, env = {}, {}
         for name, g in self.globals.items():
             key = (g["group"], g["binding"])
             if key not in bindings:
@@ -86,21 +99,45 @@ class VecShader:
             if isinstance(b, np.ndarray):
                 if b.dtype.names:
                     raise NotImplementedError("SIMT executor: arrays of structs")
-                self.arrays[name] = b
+                arrays[name] = b
                 env[name] = ("array", name)
             else:
                 env[name] = b
-        fn = self.funcs["main"]
+        d = _Dispatch(arrays, env, self.path)
+        threads = max(1, min(int(threads), n // 65536 or 1))
+        if threads == 1:
+            _Lanes(self, d, 0, n).run()
+            return
+        step = -(-n // threads)
+        chunks = [_Lanes(self, d, lo, min(lo + step, n)) for lo in range(0, n, step)]
+        own = pool is None
+        pool = pool or ThreadPoolExecutor(threads)
+        try:
+            for f in [pool.submit(c.run) for c in chunks]:
+                f.result()
+        finally:
+            if own:
+                pool.shutdown()
+
+
+class _Lanes:
+    """the invocations [lo, hi) of one dispatch, evaluated together"""
+
+    def __init__(self, shader, dispatch, lo, hi):
+        self.sh, self.d, self.lo, self.hi = shader, dispatch, lo, hi
+        self.n = hi - lo
+        self.gid = np.arange(lo, hi, dtype=u32)
+
+    def run(self):
+        fn = self.sh.funcs["main"]
         scope = {}
         for pname, _, pattrs in fn["params"]:
             if pattrs.get("builtin") == ["global_invocation_id"]:
                 scope[pname] = {"x": self.gid, "y": u32(0), "z": u32(0)}
             else:
                 raise NotImplementedError(f"WGSL: builtin {pattrs}")
-        self.env = env
         with np.errstate(all="ignore"):
-            frame = _Frame([env, scope], np.ones(n, dtype=bool))
-            self._block(fn["body"], frame)
+            self._block(fn["body"], _Frame([self.d.env, scope], np.ones(self.n, dtype=bool)))
 
     # -- statements ------------------------------------------------------------------------------------------
     def _block(self, stmts, fr):
@@ -164,24 +201,23 @@ class VecShader:
             raise NotImplementedError(f"SIMT executor: statement `{kind}`")
 
     # -- memory ----------------------------------------------------------------------------------------------
-    def _check_own(self, name, idx, active, what):
-        if idx is self.gid:
-            return
-        if not (isinstance(idx, np.ndarray) and np.array_equal(idx[active], self.gid[active])):
-            raise RuntimeError(f"SIMT executor: {what} `{name}` at another invocation's element in "
-                               f"{os.path.basename(self.path)}: result would depend on scheduling")
+    def _is_own(self, idx, active):
+        return idx is self.gid or (isinstance(idx, np.ndarray) and np.array_equal(idx[active], self.gid[active]))
 
     def _load(self, name, idx, active):
-        data = self.arrays[name]
-        if name in self.stored:
-            self._check_own(name, idx, active, "load from stored-to array")
+        data = self.d.arrays[name]
         m = len(data)
         if idx is self.gid:
-            if m >= self.n:
-                return data[:self.n].copy()
+            if m >= self.hi:
+                return data[self.lo:self.hi].copy()
             out = np.zeros(self.n, dtype=data.dtype)
-            out[:m] = data
+            if m > self.lo:
+                out[:m - self.lo] = data[self.lo:]
             return out
+        if not self._is_own(idx, active):
+            self.d.foreign.add(name)
+            if name in self.d.stored:
+                raise self.d.conflict(name)
         if not isinstance(idx, np.ndarray):
             i = int(idx)
             return data[i] if 0 <= i < m else data.dtype.type(0)
@@ -192,20 +228,23 @@ class VecShader:
         return out
 
     def _store(self, name, idx, val, active):
-        data = self.arrays[name]
-        self._check_own(name, idx, active, "store to")
-        self.stored.add(name)
-        m = min(len(data), self.n)
+        data = self.d.arrays[name]
+        if not self._is_own(idx, active):
+            raise self.d.conflict(name)
+        self.d.stored.add(name)
+        if name in self.d.foreign:
+            raise self.d.conflict(name)
+        k = max(0, min(len(data), self.hi) - self.lo)  # lanes whose own element exists: the rest is dropped
         if _is_abstract(val):
             val = data.dtype.type(val)
         if isinstance(val, np.ndarray):
             if val.dtype != data.dtype:
                 raise TypeError(f"WGSL: storing {val.dtype} into array<{data.dtype}> `{name}`")
-            np.copyto(data[:m], val[:m], where=active[:m])
+            np.copyto(data[self.lo:self.lo + k], val[:k], where=active[:k])
         else:
             if np.dtype(type(val)) != data.dtype:
                 raise TypeError(f"WGSL: storing {type(val)} into array<{data.dtype}> `{name}`")
-            data[:m][active[:m]] = val
+            data[self.lo:self.lo + k][active[:k]] = val
 
     # -- expressions -----------------------------------------------------------------------------------------
     def _lookup(self, name, fr):
@@ -291,14 +330,14 @@ class VecShader:
         raise NotImplementedError(op)
 
     def _call(self, name, args, fr):
-        if name in self.funcs:
-            fn = self.funcs[name]
+        if name in self.sh.funcs:
+            fn = self.sh.funcs[name]
             scope = {}
             for (pname, pty, _), a in zip(fn["params"], args):
                 if _is_abstract(a):
                     a = _CONCRETE[pty[0]](a)
                 scope[pname] = a
-            inner = _Frame([self.env, scope], fr.active.copy())
+            inner = _Frame([self.d.env, scope], fr.active.copy())
             self._block(fn["body"], inner)
             return inner.ret
         if name == "f32":
@@ -335,7 +374,7 @@ class WgslLBMVec(WgslLBM):
     VECTOR = ("pre_corner", "pre_cardinal", "col_cardinal", "col_corner", "ne_sw", "nw_se", "n_s", "e_w",
               "ux", "uy", "rho", "speed", "curl")
 
-    def __init__(self, omega, x, y, inflow_ux=0.1, root=None):
+    def __init__(self, omega, x, y, inflow_ux=0.1, root=None, threads=1):
         from . import wgsl_interp
         root = root or wgsl_interp.SHADER_ROOT
         super().__init__(omega, x, y, inflow_ux=inflow_ux, root=root)
@@ -347,9 +386,11 @@ class WgslLBMVec(WgslLBM):
                "uy": "summary_stats/uy.wgsl", "rho": "summary_stats/rho.wgsl", "speed": "summary_stats/speed.wgsl",
                "curl": "summary_stats/curl.wgsl"}
         self.vsh = {k: VecShader(os.path.join(root, v)) for k, v in rel.items()}
+        self.threads = int(threads)
+        self.pool = ThreadPoolExecutor(self.threads) if self.threads > 1 else None
 
     def _run(self, name, bindings):
         if name in self.vsh:
-            self.vsh[name].dispatch(self.work_groups, bindings)
+            self.vsh[name].dispatch(self.work_groups, bindings, threads=self.threads, pool=self.pool)
         else:
             self.sh[name].dispatch(self.work_groups, bindings)

@@ -4,7 +4,7 @@
 (GPU test) replay the same scripts and must reproduce every digest.
 
     python tests/golden/make_wgsl_wide.py [case ...]   # one process per case; named cases are merged into the file
-                                                       # (box_4096x4096: ~1 h and ~6 GB; the others: a minute)
+                                                       # (box_4096x4096_1000steps: ~35 min on 8 threads, ~6 GB; the others: minutes)
 """
 import os
 import sys
@@ -19,11 +19,14 @@ sys.path.insert(0, ROOT)
 from tests import wgsl_cases  # noqa: E402
 
 
+THREADS = int(os.environ.get("WGSL_SIMT_THREADS", "8"))  # host threads per large case (chunks of one dispatch)
+
+
 def run(name):
     from oracle.wgsl_simt import WgslLBMVec
     omega, w, h, u0, script = wgsl_cases.wide_cases()[name]
     t = time.time()
-    sim = WgslLBMVec(omega, w, h, inflow_ux=u0)
+    sim = WgslLBMVec(omega, w, h, inflow_ux=u0, threads=THREADS if w * h >= (1 << 22) else 1)
     shots = wgsl_cases.replay(script, sim, lambda s: wgsl_cases.digest_snapshot(s.state()))
     print(f"{name}: {len(shots)} snapshots, {time.time() - t:.0f} s", flush=True)
     return name, shots

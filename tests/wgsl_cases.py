@@ -100,6 +100,9 @@ def _porous_strip(w, h):
             ("compare",)]
 
 
+SLOW_CASE = "box_4096x4096_1000steps"
+
+
 def wide_cases():
     out = {}
     out["porous_1024x512"] = (1.0, 1024, 512, 0.05, _porous_wide(1024, 512))
@@ -108,6 +111,9 @@ def wide_cases():
     # configs[2] at its full row length (16384 cells, 15 % porous)
     out["box_4096x4096"] = (1.25, 4096, 4096, 0.1, _box(4096, 4096, steps=(1, 19, 40)))
     out["porous_16384x256"] = (1.0, 16384, 256, 0.05, _porous_strip(16384, 256))
+    # SURVEY.md 8d config 2 as specified: the 4096^2 closed box for 1,000 steps (the oracle needs ~3 minutes for it,
+    # so its CPU test only runs with BLBM_SLOW_ORACLE=1; the GPU test always runs)
+    out[SLOW_CASE] = (1.25, 4096, 4096, 0.1, _box(4096, 4096, steps=(100, 200, 700)))
     for w, h, steps in ((300, 170, 40), (1001, 37, 30), (4100, 5, 12)):
         rng = np.random.default_rng(9000 * w + h)
         out[f"random_{w}x{h}"] = (1.0 / (3 * 0.02 + 0.5), w, h, 0.1, random_script(rng, w, h, max_steps=steps))
