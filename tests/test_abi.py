@@ -140,3 +140,35 @@ def test_default_step_kernels_keep_their_register_budget_and_wide_accesses():
         assert int(res[k]["REG"]) <= 80 and int(res[k]["STACK"]) == 0
     tma = [k for n, k in names.items() if n.startswith("step_tma_kernel<")]
     assert tma and all(counts[k]["UTMALDG"] >= 9 and counts[k]["SYNCS"] > 0 and int(res[k]["STACK"]) == 0 for k in tma)
+
+
+def test_every_entry_point_rejects_a_null_handle_without_crashing():
+    """Error behaviour at the boundary: the reference panics (expect/unwrap); the C ABI must return a status.
+    Every handle-taking entry point called with NULL (and zero / NULL for the rest) returns a negative blbm_status —
+    or the neutral value for the plain getters — sets blbm_last_error, and never dereferences the handle."""
+    lib = lbm_b200.load_library()
+    getters = {"blbm_get_compute_num": 0, "blbm_get_frame_num": 0, "blbm_get_launch_count": 0,
+               "blbm_get_device_bytes": 0, "blbm_get_lazy_barriers_active": 0}
+    no_handle = {"blbm_last_error", "blbm_abi_version", "blbm_device_count", "blbm_create", "blbm_create_slab",
+                 "blbm_rasterize_line"}
+    checked = 0
+    for name, (res, args) in host.PROTOTYPES.items():
+        if name in no_handle:
+            continue
+        assert args and args[0] is host._P, name
+        zeros = [a() if a is not host._P and not hasattr(a, "contents") else None for a in args]
+        rc = getattr(lib, name)(*zeros)
+        if name == "blbm_destroy":
+            assert rc == 0  # destroying nothing is fine, like dropping an Option::None
+        elif name in getters:
+            assert rc == getters[name], name
+        else:
+            assert rc < 0, f"{name}(NULL, ...) returned {rc}"
+            assert lib.blbm_last_error(), name
+        checked += 1
+    assert checked >= 45
+    # creation with bad arguments: status, no handle
+    h = host._P()
+    assert lib.blbm_create(0, 8, 1.0, 0.1, 0, C.byref(h)) < 0 and not h
+    assert lib.blbm_create_slab(8, 8, 4, 4, 1.0, 0.1, 0, C.byref(h)) < 0 and not h
+    assert lib.blbm_create(8, 8, 1.0, 0.1, 0, None) < 0
