@@ -172,3 +172,26 @@ def test_every_entry_point_rejects_a_null_handle_without_crashing():
     assert lib.blbm_create(0, 8, 1.0, 0.1, 0, C.byref(h)) < 0 and not h
     assert lib.blbm_create_slab(8, 8, 4, 4, 1.0, 0.1, 0, C.byref(h)) < 0 and not h
     assert lib.blbm_create(8, 8, 1.0, 0.1, 0, None) < 0
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/blbm.h must compile as C99 (what cgo / bindgen / a Rust -sys crate's
+    build script would feed it to), and a C program using it must link against the library."""
+    import subprocess
+    import tempfile
+    hdr = os.path.join(ROOT, "include", "blbm.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = ('#include "blbm.h"\n#include <stdio.h>\n'
+           "int main(void) { blbm_t *h = 0; int rc = blbm_create(64, 32, 1.25f, 0.1f, 0, &h);\n"
+           '  printf("%d %d %s\\n", blbm_abi_version(), rc, blbm_last_error()); if (h) blbm_destroy(h); return 0; }\n')
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(c, "w").write(src)
+        libdir = os.path.dirname(lbm_b200.library_path())
+        r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe, "-L", libdir, "-lblbm",
+                            f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.startswith("1 "), r.stdout + r.stderr
