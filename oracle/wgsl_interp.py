@@ -330,6 +330,7 @@ class StorageArray:
 
 class Shader:
     def __init__(self, path_or_src, is_source=False):
+        self.path = None if is_source else path_or_src
         src = path_or_src if is_source else open(path_or_src).read()
         self.structs, self.globals, self.funcs = Parser(src).module()
         if "main" not in self.funcs or "compute" not in self.funcs["main"]["attrs"]:
