@@ -1,0 +1,175 @@
+"""Generates tests/golden/wasm_golden.npz by EXECUTING HOST-SIDE FUNCTIONS OF THE REFERENCE'S OWN SHIPPED BINARY
+(/root/reference/lbm-wgpu/pkg/lbm_wgpu_bg.wasm, the wasm-pack build of lbm-wgpu) in oracle/wasm_mini.py:
+
+  * `set_equil` (lbm.rs:611-643; rustc specialised it to uy = 0, rho = 1, the only values lbm.rs ever passes):
+    the nine initial populations for a list of inflow speeds — row a-2 of SURVEY.md section 8;
+  * `Line::new` (barrier_shapes/line.rs:22-54) called directly, and `Line::new_erased` (line.rs:56-87, the 30-wide
+    eraser) and `Line::new` again through `Curve::erase_segment` / `Curve::add_segment` (curve.rs:28-48): the
+    point sets of thick lines, with the un-vendored `line_drawing 1.0.0` Bresenham as compiled into the binary —
+    row N2 (the rasteriser in front of draw_points).
+
+The binary carries no name section, so the functions are addressed by index and each index is checked against a
+fingerprint (signature, floating-point constants, the "Endpoints (" format string it refers to, its callees) before
+it is trusted; the SHA-256 of the binary is stored with the results.  None of these functions touches an import on
+its normal path (std's HashSet keys are constants on wasm32-unknown-unknown), so no browser is needed.
+
+    python tests/golden/make_wasm_golden.py        # build container only (needs /root/reference); ~1 minute
+"""
+import hashlib
+import os
+import struct
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.wasm_mini import Instance, Module  # noqa: E402
+
+WASM = "/root/reference/lbm-wgpu/pkg/lbm_wgpu_bg.wasm"
+F_SET_EQUIL, F_LINE_NEW, F_ERASE_SEGMENT, F_ADD_SEGMENT = 268, 249, 307, 308
+I32, F32 = 0x7F, 0x7D
+
+INFLOWS = (0.1, 0.05, 0.0, 0.07, 0.03, 0.3, -0.1, 0.2)
+
+
+def line_cases():
+    """(p1, p2, xdim, ydim): every octant, axis-aligned, degenerate, border-to-border, and random pairs"""
+    c = []
+    for xd, yd in ((64, 32), (512, 256)):
+        mx, my = xd - 1, yd - 1
+        pairs = [((3, 4), (20, 11)), ((20, 11), (3, 4)), ((5, 5), (5, 5)), ((0, 0), (mx, my)), ((mx, 0), (0, my)),
+                 ((10, 3), (10, my - 2)), ((2, 9), (mx - 3, 9)), ((7, my - 1), (8, 2)), ((0, 0), (0, 0)),
+                 ((mx, my), (mx, my)), ((1, 1), (2, 2)), ((1, 2), (2, 1)), ((30, 3), (33, 28)), ((33, 28), (30, 3)),
+                 ((4, 20), (40, 17)), ((40, 17), (4, 20)), ((0, my), (mx, my)), ((mx, 0), (mx, my))]
+        rng = np.random.default_rng(1000 + xd)
+        for _ in range(30):
+            pairs.append(((int(rng.integers(0, xd)), int(rng.integers(0, yd))),
+                          (int(rng.integers(0, xd)), int(rng.integers(0, yd)))))
+        c += [(a, b, xd, yd) for a, b in pairs]
+    # invalid end points: Line::new returns Err
+    c += [((3, 4), (64, 11), 64, 32), ((-1, 4), (10, 11), 64, 32), ((3, 32), (10, 11), 64, 32)]
+    return c
+
+
+def check_fingerprints(m):
+    def consts(f, op):
+        return {i[1] for i in m.decode(f)[1] if i[0] == op}
+
+    def calls(f):
+        return {i[1] for i in m.decode(f)[1] if i[0] == 0x10}
+
+    endpoints = None
+    for off, blob in m.segments:
+        k = blob.find(b"Endpoints (")
+        if k >= 0:
+            endpoints = off + k
+    assert endpoints is not None
+    # the format-pieces table right behind the string starts with (ptr to "Endpoints (", 11)
+    pieces = None
+    for off, blob in m.segments:
+        k = blob.find(struct.pack("<II", endpoints, 11))
+        if k >= 0:
+            pieces = off + k
+    assert pieces is not None
+    assert m.type_of(F_SET_EQUIL) == ([I32, F32, I32, I32], [])
+    f = consts(F_SET_EQUIL, 0x43)
+    assert {4.5, 1.5, 3.0, 1.0}.issubset(f)
+    assert float(np.float32(1.0) / np.float32(36.0)) in f and float(np.float32(1.0) / np.float32(9.0)) in f
+    assert m.type_of(F_LINE_NEW) == ([I32] * 7, []) and pieces in consts(F_LINE_NEW, 0x41)
+    assert m.type_of(F_ERASE_SEGMENT) == ([I32] * 5, []) and pieces in consts(F_ERASE_SEGMENT, 0x41)
+    assert m.type_of(F_ADD_SEGMENT) == ([I32] * 5, []) and F_LINE_NEW in calls(F_ADD_SEGMENT)
+    assert F_LINE_NEW not in calls(F_ERASE_SEGMENT)  # new_erased is inlined there
+    # hashbrown's static empty control group, referenced where the functions create an empty HashSet
+    empty = [c for c in consts(F_LINE_NEW, 0x41) if 1 << 20 <= c < 1 << 21 and
+             any(off <= c < off + len(b) and b[c - off:c - off + 4] == b"\xff" * 4 for off, b in m.segments)]
+    assert len(empty) == 1
+    return empty[0]
+
+
+class Reference:
+    """the shipped binary, its located functions and the calling conventions found by inspection"""
+
+    def __init__(self, path=WASM):
+        self.blob = open(path, "rb").read()
+        self.sha256 = hashlib.sha256(self.blob).hexdigest()
+        self.m = Module(self.blob)
+        self.empty_group = check_fingerprints(self.m)
+        self.stubs = {n: (lambda inst, *a: 37) if self.m.types[t][1] else (lambda inst, *a: None)
+                      for _, n, t in self.m.imports}
+
+    def _instance(self, frame=64):
+        inst = Instance(self.m, imports=self.stubs)
+        base = inst.globals[0] - frame  # a frame on the shadow stack for the out-parameter
+        inst.globals[0] = base
+        return inst, base
+
+    def set_equil(self, ux, x=5, y=3):
+        """fn set_equil(ux, uy = 0, rho = 1, x, y) -> Vec<Vec<f32>>: nine vectors of x*y equal values"""
+        inst, ret = self._instance()
+        inst.call(F_SET_EQUIL, ret, float(np.float32(ux)), x, y)
+        cap, ptr, n = inst.u32(ret), inst.u32(ret + 4), inst.u32(ret + 8)
+        assert n == 9 and not inst.called
+        out = np.zeros(9, np.float32)
+        for k in range(9):
+            p, ln = inst.u32(ptr + 12 * k + 4), inst.u32(ptr + 12 * k + 8)
+            v = np.frombuffer(inst.read(p, 4 * ln), dtype=np.float32)
+            assert ln == x * y and (v.view(np.uint32) == v.view(np.uint32)[0]).all()
+            out[k] = v[0]
+        return out
+
+    @staticmethod
+    def _read_set(inst, base):
+        """HashSet<(isize, isize, bool)> = RandomState {k0, k1: u64} + RawTable {bucket_mask, growth_left, items, ctrl};
+        12-byte elements lie below ctrl, element i at ctrl - 12 (i + 1); a control byte with the top bit clear = full"""
+        mask, _, items, ctrl = (inst.u32(base + 16 + 4 * k) for k in range(4))
+        if ctrl == 0:
+            return None  # Err(String): the niche of the control pointer
+        pts = []
+        for i in range(mask + 1):
+            if inst.mem[ctrl + i] & 0x80 == 0:
+                a = ctrl - 12 * (i + 1)
+                pts.append((inst.i32(a), inst.i32(a + 4), inst.mem[a + 8]))
+        assert len(pts) == items == len(set(pts))
+        return sorted(pts)
+
+    def line_new(self, p1, p2, xdim, ydim):
+        inst, ret = self._instance()
+        inst.call(F_LINE_NEW, ret, *(v & 0xFFFFFFFF for v in (p1[0], p1[1], p2[0], p2[1], xdim, ydim)))
+        return self._read_set(inst, ret)
+
+    def curve_segment(self, erase, p1, p2, xdim, ydim):
+        """Curve { points: empty, last_point: Some(p1) }.erase_segment(p2, ..) / .add_segment(p2, ..)"""
+        inst, cur = self._instance()
+        struct.pack_into("<QQIIIIIii", inst.mem, cur, 1, 2, 0, 0, 0, self.empty_group, 1, p1[0], p1[1])
+        inst.call(F_ERASE_SEGMENT if erase else F_ADD_SEGMENT, cur, p2[0] & 0xFFFFFFFF, p2[1] & 0xFFFFFFFF, xdim, ydim)
+        assert (inst.i32(cur + 36), inst.i32(cur + 40)) == tuple(p2)  # last_point = Some(next)
+        return self._read_set(inst, cur)
+
+
+def main():
+    ref = Reference()
+    out = {"wasm_sha256": np.bytes_(ref.sha256), "inflows": np.array(INFLOWS, np.float32)}
+    out["set_equil"] = np.stack([ref.set_equil(u) for u in INFLOWS])
+    cases = line_cases()
+    out["line_cases"] = np.array([[a[0], a[1], b[0], b[1], xd, yd] for a, b, xd, yd in cases], np.int64)
+    for i, (a, b, xd, yd) in enumerate(cases):
+        pts = ref.line_new(a, b, xd, yd)
+        if pts is None:
+            out[f"line/{i}/new"] = np.zeros((0, 3), np.int32)  # Err(..): a valid line has at least one cell
+            continue
+        out[f"line/{i}/new"] = np.array(pts, np.int32).reshape(-1, 3)
+        seg = ref.curve_segment(False, a, b, xd, yd)
+        assert seg == pts, "Curve::add_segment must give Line::new's points"
+        if i % 3 == 0 or xd == 64:  # the 30-wide eraser is slow to interpret: a subset of the cases
+            out[f"line/{i}/erased"] = np.array(ref.curve_segment(True, a, b, xd, yd), np.int32).reshape(-1, 3)
+        print(f"case {i}: {a} -> {b} on {xd}x{yd}: {len(pts)} cells", flush=True)
+    path = os.path.join(HERE, "wasm_golden.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+"""Parity pinned to OUTPUTS OF THE REFERENCE ITSELF for its host-side rows.
+
+tests/golden/wasm_golden.npz holds the results of executing functions of the reference's own shipped binary
+(lbm-wgpu/pkg/lbm_wgpu_bg.wasm, run in oracle/wasm_mini.py by tests/golden/make_wasm_golden.py):
+  * `set_equil` (lbm.rs:611-643) -> the nine initial populations for eight inflow speeds   
+  * `Line::new` / `Line::new_erased` (barrier_shapes/line.rs:22-87, with the un-vendored line_drawing 1.0.0
+    Bresenham as compiled in) -> the cells of 99 thick lines on two lattice sizes           (row N2)
+Here the oracle's restatements, the product's host-side rasteriser (libblbm.so: blbm_rasterize_line is pure host
+code and runs without a GPU) and, on the GPU, the initial state and the painted mask of the CUDA path are compared
+with them.  Where /root/reference exists the binary is re-run live."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import barrier_shapes
+from oracle.lbm_oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "wasm_golden.npz")
+WASM = "/root/reference/lbm-wgpu/pkg/lbm_wgpu_bg.wasm"
+needs_reference = pytest.mark.skipif(not os.path.exists(WASM), reason="/root/reference is only present in the build container")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def cases(golden):
+    for i, (x1, y1, x2, y2, xd, yd) in enumerate(golden["line_cases"].tolist()):
+        yield i, (x1, y1), (x2, y2), xd, yd
+
+
+def cells(a):
+    return sorted(map(tuple, np.asarray(a)[:, :2].tolist()))
+
+
+def test_oracle_initial_populations_equal_the_reference_binarys_set_equil(golden):
+    """the C oracle, the numpy restatement and the WGSL driver's host-side set_equil against the compiled one"""
+    from oracle.lbm_numpy import NumpyLBM
+    from oracle.wgsl_interp import WgslLBM
+    for ux, want in zip(golden["inflows"], golden["set_equil"]):
+        o = Oracle(1.0, 6, 5, inflow_ux=float(ux))
+        got = np.array([o.population(0, k).ravel()[7] for k in range(9)], np.float32)
+        assert (bits(got) == bits(want)).all(), (ux, got, want)
+        for b in (0, 1):
+            for k in range(9):
+                assert (bits(o.population(b, k)) == bits(want[k])).all()
+        o.close()
+        w = np.array(WgslLBM.set_equil(np.float32(ux), np.float32(0), np.float32(1)), np.float32)
+        assert (bits(w) == bits(want)).all()
+        n = NumpyLBM(1.0, 6, 5, inflow_ux=float(ux))
+        assert all((bits(n.population(0, k)) == bits(want[k])).all() for k in range(9))
+
+
+def test_host_rasteriser_equals_the_reference_binarys_lines(golden):
+    """libblbm.so's blbm_rasterize_line (the product's host code in front of draw_points) and the oracle's
+    restatement against Line::new / Line::new_erased as compiled into the reference's binary"""
+    from lbm_b200.lbm import rasterize_line
+    n_new = n_erased = n_err = 0
+    for i, p1, p2, xd, yd in cases(golden):
+        want = golden[f"line/{i}/new"]
+        ours = rasterize_line(p1, p2, xd, yd, erase=False)
+        ora = barrier_shapes.line_points(p1, p2, xd, yd, erase=False)
+        if len(want) == 0:  # the reference returned Err(..)
+            assert ours is None and ora is None
+            n_err += 1
+            continue
+        assert (want[:, 2] == 1).all()
+        assert cells(ours) == cells(want), f"Line::new {p1}->{p2} on {xd}x{yd}"
+        assert sorted((x, y) for x, y, *_ in ora) == cells(want)
+        n_new += 1
+        key = f"line/{i}/erased"
+        if key in golden.files:
+            want = golden[key]
+            assert (want[:, 2] == 0).all()
+            assert cells(rasterize_line(p1, p2, xd, yd, erase=True)) == cells(want), f"Line::new_erased {p1}->{p2}"
+            assert sorted((x, y) for x, y, *_ in barrier_shapes.line_points(p1, p2, xd, yd, erase=True)) == cells(want)
+            n_erased += 1
+    assert n_new >= 90 and n_erased >= 50 and n_err == 3
+
+
+@needs_reference
+def test_fixture_comes_from_the_binary_in_the_reference_tree_and_reruns_live(golden):
+    from tests.golden.make_wasm_golden import Reference
+    ref = Reference()  # checks the fingerprints of the four functions
+    assert ref.sha256 == golden["wasm_sha256"].item().decode()
+    for ux, want in list(zip(golden["inflows"], golden["set_equil"]))[:3]:
+        assert (bits(ref.set_equil(ux)) == bits(want)).all()
+    for i, p1, p2, xd, yd in list(cases(golden))[:4]:
+        assert np.array_equal(np.array(ref.line_new(p1, p2, xd, yd), np.int32).reshape(-1, 3), golden[f"line/{i}/new"])
+    i, p1, p2, xd, yd = list(cases(golden))[-1]
+    assert ref.line_new(p1, p2, xd, yd) is None and len(golden[f"line/{i}/new"]) == 0
+
+
+def test_wasm_interpreter_arithmetic():
+    """the interpreter itself, on a hand-assembled module: i32 wrap-around, signed division and comparison,
+    shifts, a loop with br_if, memory round trip, f32 rounding"""
+    from oracle.wasm_mini import Instance, Module, Trap
+
+    def leb(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            if (v == 0 and not b & 0x40) or (v == -1 and b & 0x40):
+                return bytes(out + bytes([b]))
+            out.append(b | 0x80)
+
+    def func(locals_, body):
+        code = bytes([len(locals_)]) + b"".join(bytes([n, t]) for n, t in locals_) + body + b"\x0b"
+        return leb(len(code)) + code
+
+    I, F = 0x7F, 0x7D
+    # f0(a, b) = a / b (signed) + (a < b signed); f1(n) = sum_{k<n} k*k via a loop; f2(x, y) = x * y + 0.1 (f32), through memory
+    f0 = func([], b"\x20\x00\x20\x01\x6d\x20\x00\x20\x01\x48\x6a")
+    f1 = func([(2, I)], b"\x03\x40" + b"\x20\x01\x20\x02\x20\x02\x6c\x6a\x21\x01" + b"\x20\x02\x41\x01\x6a\x22\x02\x20\x00\x49\x0d\x00" + b"\x0b\x20\x01")
+    f2 = func([], b"\x41\x10\x20\x00\x20\x01\x94\x38\x02\x00\x41\x10\x2a\x02\x00\x43" + np.float32(0.1).tobytes() + b"\x92")
+    types = b"\x03" + b"\x60\x02\x7f\x7f\x01\x7f" + b"\x60\x01\x7f\x01\x7f" + b"\x60\x02\x7d\x7d\x01\x7d"
+    sec = lambda sid, body: bytes([sid]) + leb(len(body)) + body  # noqa: E731
+    mod = (b"\x00asm\x01\x00\x00\x00" + sec(1, types) + sec(3, b"\x03\x00\x01\x02") + sec(5, b"\x01\x00\x01") +
+           sec(10, b"\x03" + f0 + f1 + f2))
+    inst = Instance(Module(mod))
+    assert inst.call(0, (-7) & 0xFFFFFFFF, 2) == ((-3) + 1) & 0xFFFFFFFF  # trunc toward zero, -7 < 2 signed
+    assert inst.call(0, 7, (-2) & 0xFFFFFFFF) == (-3) & 0xFFFFFFFF
+    with pytest.raises(Trap):
+        inst.call(0, 1, 0)
+    assert inst.call(1, 10) == sum(k * k for k in range(10))
+    x, y = np.float32(1.1), np.float32(3.3)
+    assert np.float32(inst.call(2, float(x), float(y))).view(np.uint32) == (x * y + np.float32(0.1)).view(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_cuda_initial_state_equals_the_reference_binarys_set_equil(golden):
+    from lbm_b200 import LBM
+    for ux, want in zip(golden["inflows"], golden["set_equil"]):
+        lbm = LBM(1.0, 70, 9, inflow_ux=float(ux))
+        for b in (0, 1):
+            for k in range(9):
+                assert (bits(lbm.read_population(k, b)) == bits(want[k])).all(), (ux, b, k)
+        lbm.custom_speed(float(ux))
+        for k in range(9):
+            assert (bits(lbm.read_population(k, 0)) == bits(want[k])).all(), ("custom_speed", ux, k)
+        lbm.close()
+
+
+@pytest.mark.gpu
+def test_cuda_draw_line_paints_the_reference_binarys_cells(golden):
+    """blbm_draw_line / blbm_erase_line (draw_shape(&Line::new(..)) / draw_shape(&Line::new_erased(..))) on the device
+    mask against the cells the reference's binary produced"""
+    from lbm_b200 import LBM
+    done = 0
+    for i, p1, p2, xd, yd in cases(golden):
+        want = golden[f"line/{i}/new"]
+        if xd != 64 or len(want) == 0 or i % 2:
+            continue
+        lbm = LBM(1.0, xd, yd)
+        base = lbm.read_barrier().copy()
+        lbm.draw_line(p1, p2)
+        expect = base.copy()
+        expect[want[:, 1], want[:, 0]] = 1
+        assert np.array_equal(lbm.read_barrier(), expect), f"draw_line {p1}->{p2}"
+        key = f"line/{i}/erased"
+        if key in golden.files:
+            er = golden[key]
+            lbm.erase_line(p1, p2)
+            expect[er[:, 1], er[:, 0]] = 0
+            assert np.array_equal(lbm.read_barrier(), expect), f"erase_line {p1}->{p2}"
+        lbm.close()
+        done += 1
+    assert done >= 10
