@@ -3,6 +3,9 @@
 
   * `set_equil` (lbm.rs:611-643; rustc specialised it to uy = 0, rho = 1, the only values lbm.rs ever passes):
     the nine initial populations for a list of inflow speeds — row a-2 of SURVEY.md section 8;
+  * `LBM::single_cell` (lbm.rs:1502-1515, with `set_single_cell` :1482-1500 inlined) on a fabricated `LBM` value,
+    its 18 `queue.write_buffer` calls intercepted: which population is set to 4.0 at which cell for every preset
+    index, and what every other cell holds — row a-8;
   * `Line::new` (barrier_shapes/line.rs:22-54) called directly, and `Line::new_erased` (line.rs:56-87, the 30-wide
     eraser) and `Line::new` again through `Curve::erase_segment` / `Curve::add_segment` (curve.rs:28-48): the
     point sets of thick lines, with the un-vendored `line_drawing 1.0.0` Bresenham as compiled into the binary —
@@ -26,10 +29,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from oracle.wasm_mini import Instance, Module  # noqa: E402
+from oracle.wasm_mini import Instance, Module, Trap  # noqa: E402
 
 WASM = "/root/reference/lbm-wgpu/pkg/lbm_wgpu_bg.wasm"
 F_SET_EQUIL, F_LINE_NEW, F_ERASE_SEGMENT, F_ADD_SEGMENT = 268, 249, 307, 308
+F_SINGLE_CELL, F_WRITE_BUFFER = 247, 591
+# struct LBM as laid out in this build (read off the code of LBM::single_cell): xdim, ydim, data_buffers {ptr, len};
+# a wgpu::Buffer is 88 bytes, the wgpu::Queue sits 128 bytes into Driver
+LBM_X, LBM_Y, LBM_BUFFERS_PTR, LBM_BUFFERS_LEN, SIZEOF_BUFFER, DRIVER_QUEUE = 1100, 1104, 1160, 1164, 88, 128
+SINGLE_CELL_SIZES = ((16, 12), (64, 32), (30, 17), (9, 7))
 I32, F32 = 0x7F, 0x7D
 
 INFLOWS = (0.1, 0.05, 0.0, 0.07, 0.03, 0.3, -0.1, 0.2)
@@ -82,6 +90,12 @@ def check_fingerprints(m):
     assert m.type_of(F_ERASE_SEGMENT) == ([I32] * 5, []) and pieces in consts(F_ERASE_SEGMENT, 0x41)
     assert m.type_of(F_ADD_SEGMENT) == ([I32] * 5, []) and F_LINE_NEW in calls(F_ADD_SEGMENT)
     assert F_LINE_NEW not in calls(F_ERASE_SEGMENT)  # new_erased is inlined there
+    # single_cell(&mut self, &driver, index): one set_equil, then 18 write_buffer calls; 4.0 is stored as its bit pattern
+    code = m.decode(F_SINGLE_CELL)[1]
+    assert m.type_of(F_SINGLE_CELL) == ([I32] * 3, []) and m.type_of(F_WRITE_BUFFER) == ([I32] * 4, [])
+    assert [i[1] for i in code if i[0] == 0x10].count(F_SET_EQUIL) == 1
+    assert [i[1] for i in code if i[0] == 0x10].count(F_WRITE_BUFFER) >= 18
+    assert 0x40800000 in consts(F_SINGLE_CELL, 0x41)
     # hashbrown's static empty control group, referenced where the functions create an empty HashSet
     empty = [c for c in consts(F_LINE_NEW, 0x41) if 1 << 20 <= c < 1 << 21 and
              any(off <= c < off + len(b) and b[c - off:c - off + 4] == b"\xff" * 4 for off, b in m.segments)]
@@ -135,6 +149,37 @@ class Reference:
         assert len(pts) == items == len(set(pts))
         return sorted(pts)
 
+    def single_cell(self, index, x, y):
+        """LBM::single_cell(&mut self, &driver, index) on an LBM whose only meaningful fields are xdim, ydim and
+        data_buffers (2 x 9 dummy wgpu::Buffer values); returns data[b][k] = the array uploaded to data_buffers[b][k]"""
+        got = {}
+        inst = None
+
+        def write_buffer(inst_, queue, buffer, ptr, nbytes):
+            b, k = divmod((buffer - bufs) // SIZEOF_BUFFER, 9)
+            assert queue == drv + DRIVER_QUEUE and (buffer - bufs) % SIZEOF_BUFFER == 0 and (b, k) not in got
+            got[(b, k)] = np.frombuffer(inst_.read(ptr, nbytes), dtype=np.float32).copy()
+
+        inst = Instance(self.m, imports=self.stubs, hooks={F_WRITE_BUFFER: write_buffer})
+        malloc = self.m.exports["__wbindgen_malloc"][1]
+        me = inst.call(malloc, 2048, 8)
+        drv = inst.call(malloc, 1024, 8)
+        bufs = inst.call(malloc, 18 * SIZEOF_BUFFER, 8)
+        outer = inst.call(malloc, 24, 4)
+        for a, n in ((me, 2048), (drv, 1024), (bufs, 18 * SIZEOF_BUFFER)):
+            inst.mem[a:a + n] = bytes(n)
+        struct.pack_into("<IIIIII", inst.mem, outer, 9, bufs, 9, 9, bufs + 9 * SIZEOF_BUFFER, 9)  # two Vec {cap, ptr, len}
+        struct.pack_into("<II", inst.mem, me + LBM_X, x, y)
+        struct.pack_into("<II", inst.mem, me + LBM_BUFFERS_PTR, outer, 2)
+        try:
+            inst.call(F_SINGLE_CELL, me, drv, index)
+        except Trap:
+            # after the 18 uploads single_cell creates and submits an EMPTY command encoder through the device's
+            # `dyn Context` (lbm.rs:1511-1514): an indirect call our zeroed Driver cannot serve.  All data is out by then.
+            pass
+        assert len(got) == 18 and all(len(v) == x * y for v in got.values()) and not inst.called
+        return np.stack([np.stack([got[(b, k)] for k in range(9)]) for b in range(2)]).reshape(2, 9, y, x)
+
     def line_new(self, p1, p2, xdim, ydim):
         inst, ret = self._instance()
         inst.call(F_LINE_NEW, ret, *(v & 0xFFFFFFFF for v in (p1[0], p1[1], p2[0], p2[1], xdim, ydim)))
@@ -153,6 +198,11 @@ def main():
     ref = Reference()
     out = {"wasm_sha256": np.bytes_(ref.sha256), "inflows": np.array(INFLOWS, np.float32)}
     out["set_equil"] = np.stack([ref.set_equil(u) for u in INFLOWS])
+    for x, y in SINGLE_CELL_SIZES:
+        for index in range(10):
+            out[f"single_cell/{x}x{y}/{index}"] = ref.single_cell(index, x, y)
+        print(f"single_cell on {x}x{y}: 10 presets", flush=True)
+    out["single_cell_sizes"] = np.array(SINGLE_CELL_SIZES, np.int64)
     cases = line_cases()
     out["line_cases"] = np.array([[a[0], a[1], b[0], b[1], xd, yd] for a, b, xd, yd in cases], np.int64)
     for i, (a, b, xd, yd) in enumerate(cases):

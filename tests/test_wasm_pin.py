@@ -3,6 +3,7 @@
 tests/golden/wasm_golden.npz holds the results of executing functions of the reference's own shipped binary
 (lbm-wgpu/pkg/lbm_wgpu_bg.wasm, run in oracle/wasm_mini.py by tests/golden/make_wasm_golden.py):
   * `set_equil` (lbm.rs:611-643) -> the nine initial populations for eight inflow speeds   
+  * `LBM::single_cell` (lbm.rs:1482-1515) -> the 18 arrays it uploads, for every preset index on four lattice sizes (row a-8)
   * `Line::new` / `Line::new_erased` (barrier_shapes/line.rs:22-87, with the un-vendored line_drawing 1.0.0
     Bresenham as compiled in) -> the cells of 99 thick lines on two lattice sizes           (row N2)
 Here the oracle's restatements, the product's host-side rasteriser (libblbm.so: blbm_rasterize_line is pure host
@@ -58,6 +59,31 @@ def test_oracle_initial_populations_equal_the_reference_binarys_set_equil(golden
         assert all((bits(n.population(0, k)) == bits(want[k])).all() for k in range(9))
 
 
+def single_cell_cases(golden):
+    for x, y in golden["single_cell_sizes"].tolist():
+        for index in range(10):
+            yield x, y, index, golden[f"single_cell/{x}x{y}/{index}"]  # [buffer][population][y][x]
+
+
+def test_oracle_single_cell_equals_what_the_reference_binary_uploads(golden):
+    """LBM::single_cell as compiled: which population holds the 4.0 packet at which cell, everything else
+    set_equil(0, 0, 1); the reference uploads the rest population to both data_buffers[b][4], of which only
+    buffer 0's is ever bound (lbm.rs:775-778) — the oracle keeps that one"""
+    n = 0
+    for x, y, index, want in single_cell_cases(golden):
+        assert (bits(want[0]) == bits(want[1])).all()
+        o = Oracle(1.0, x, y)
+        o.iterate(3)
+        o.single_cell(index)
+        for b in (0, 1):
+            for k in range(9):
+                assert (bits(np.asarray(o.population(b, k)).reshape(y, x)) == bits(want[b, k])).all(), (x, y, index, b, k)
+        assert o.get_compute_num() == 0
+        o.close()
+        n += 1
+    assert n == 40
+
+
 def test_host_rasteriser_equals_the_reference_binarys_lines(golden):
     """libblbm.so's blbm_rasterize_line (the product's host code in front of draw_points) and the oracle's
     restatement against Line::new / Line::new_erased as compiled into the reference's binary"""
@@ -92,6 +118,7 @@ def test_fixture_comes_from_the_binary_in_the_reference_tree_and_reruns_live(gol
     assert ref.sha256 == golden["wasm_sha256"].item().decode()
     for ux, want in list(zip(golden["inflows"], golden["set_equil"]))[:3]:
         assert (bits(ref.set_equil(ux)) == bits(want)).all()
+    assert (bits(ref.single_cell(2, 9, 7)) == bits(golden["single_cell/9x7/2"])).all()
     for i, p1, p2, xd, yd in list(cases(golden))[:4]:
         assert np.array_equal(np.array(ref.line_new(p1, p2, xd, yd), np.int32).reshape(-1, 3), golden[f"line/{i}/new"])
     i, p1, p2, xd, yd = list(cases(golden))[-1]
@@ -147,6 +174,20 @@ def test_cuda_initial_state_equals_the_reference_binarys_set_equil(golden):
         lbm.custom_speed(float(ux))
         for k in range(9):
             assert (bits(lbm.read_population(k, 0)) == bits(want[k])).all(), ("custom_speed", ux, k)
+        lbm.close()
+
+
+@pytest.mark.gpu
+def test_cuda_single_cell_equals_what_the_reference_binary_uploads(golden):
+    from lbm_b200 import LBM
+    for x, y, index, want in single_cell_cases(golden):
+        lbm = LBM(1.0, x, y)
+        lbm.iterate(3)
+        lbm.single_cell(index)
+        for b in (0, 1):
+            for k in range(9):
+                assert (bits(lbm.read_population(k, b)) == bits(want[b, k])).all(), (x, y, index, b, k)
+        assert lbm.get_compute_num() == 0
         lbm.close()
 
 
