@@ -1022,26 +1022,26 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
     if (!pairs) return fail(BLBM_EINVAL, "pairs is null");
     // keep, per location, the last pair (sequential scatter semantics), then upload what touches this slab
     std::vector<std::pair<uint64_t, uint64_t>> idx;  // (location, position)
-    try {
+    std::vector<uint64_t> uniq;
+    try {  // no C++ exception may cross the C ABI
         idx.reserve(npairs);
+        const uint64_t total = (uint64_t)h->W * h->Hg;
+        const uint64_t lo = (h->row0 >= 2 ? h->row0 - 2 : 0) * (uint64_t)h->W;
+        const uint64_t hi = std::min<uint64_t>(h->Hg, h->row1 + 2) * (uint64_t)h->W;
+        for (size_t p = 0; p < npairs; p++) {
+            const uint64_t loc = pairs[2 * p];
+            if (loc >= total || loc < lo || loc >= hi) continue;
+            idx.emplace_back(loc, (uint64_t)p);
+        }
+        std::sort(idx.begin(), idx.end());
+        uniq.reserve(idx.size() * 2);
+        for (size_t q = 0; q < idx.size(); q++) {
+            if (q + 1 < idx.size() && idx[q + 1].first == idx[q].first) continue;
+            uniq.push_back(idx[q].first);
+            uniq.push_back(pairs[2 * idx[q].second + 1]);
+        }
     } catch (...) {
         return fail(BLBM_ENOMEM, "out of host memory");
-    }
-    const uint64_t total = (uint64_t)h->W * h->Hg;
-    const uint64_t lo = (h->row0 >= 2 ? h->row0 - 2 : 0) * (uint64_t)h->W;
-    const uint64_t hi = std::min<uint64_t>(h->Hg, h->row1 + 2) * (uint64_t)h->W;
-    for (size_t p = 0; p < npairs; p++) {
-        const uint64_t loc = pairs[2 * p];
-        if (loc >= total || loc < lo || loc >= hi) continue;
-        idx.emplace_back(loc, (uint64_t)p);
-    }
-    std::sort(idx.begin(), idx.end());
-    std::vector<uint64_t> uniq;
-    uniq.reserve(idx.size() * 2);
-    for (size_t q = 0; q < idx.size(); q++) {
-        if (q + 1 < idx.size() && idx[q + 1].first == idx[q].first) continue;
-        uniq.push_back(idx[q].first);
-        uniq.push_back(pairs[2 * idx[q].second + 1]);
     }
     const size_t nu = uniq.size() / 2;
     // owned rows whose class words depend on the painted cells: a cell at row y is an upstream neighbour of
@@ -1270,10 +1270,11 @@ int blbm_read_cell_class(blbm_t *h, uint16_t *dst)
         cudaGetLastError();
         return fail(BLBM_ENOMEM, "allocating %zu bytes for the class read-back failed", bytes);
     }
-    CK(launch_build_public_class(tmp, h->mask, geom(h), h->stream));
+    cudaError_t e = launch_build_public_class(tmp, h->mask, geom(h), h->stream);
     h->launches++;
-    CK(cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, h->stream));
-    stream_free(tmp, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
+    stream_free(tmp, h->stream);  // stream-ordered: released after the copy, also on the error path
+    if (e != cudaSuccess) return fail(BLBM_ECUDA, "class read-back failed: %s", cudaGetErrorString(e));
     return sync_stream(h);
 }
 
