@@ -11,8 +11,8 @@ global_invocation_id.x) and every load from an array that the dispatch also stor
 in program order — reads the invocation's own element (`_check_own`, `_Dispatch.stored / foreign`).  Then no
 invocation can observe another one's stores and the result does not depend on scheduling; for the same reason
 the invocations may be split into contiguous chunks that run on several host threads (`threads=`; numpy releases
-the GIL inside array operations).  All step / summary shaders of the reference have that property; the scatter of
-barrier_draw.wgsl and the vec3 colour maps stay with the scalar interpreter.
+the GIL inside array operations).  All step, summary and colour-map shaders of the reference have that property; the
+scatter of barrier_draw.wgsl stays with the scalar interpreter.
 
 Semantics (identical to wgsl_interp.py and to the oracle's normative block): every fp32
 operation individually rounded (numpy float32 element-wise arithmetic; IEEE division and sqrt), u32 arithmetic
@@ -52,6 +52,13 @@ def _is_int(v):
     if isinstance(v, np.ndarray):
         return v.dtype.kind in "iu"
     return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
+
+
+class Vec3:
+    """vec3<T>: three components, each a per-lane array or a uniform / abstract scalar"""
+
+    def __init__(self, comps):
+        self.c = list(comps)
 
 
 class _Frame:
@@ -178,6 +185,29 @@ class _Lanes:
             elif s[3] is None:
                 after |= not_taken
             fr.active = after
+        elif kind == "switch":
+            sel = self._eval(s[1], fr)
+            before = fr.active
+            matched = np.zeros_like(before)
+            after = np.zeros_like(before)
+            for vals, body in s[2]:
+                hit = np.zeros_like(before)
+                for v in vals:
+                    hit |= np.asarray(self._binop("==", sel, self._eval(v, fr)), dtype=bool)
+                hit &= before & ~matched  # the first matching clause wins
+                matched |= hit
+                if hit.any():
+                    fr.active = hit
+                    self._block(body, fr)
+                    after |= fr.active
+            rest = before & ~matched
+            if s[3] is not None and rest.any():
+                fr.active = rest
+                self._block(s[3], fr)
+                after |= fr.active
+            elif s[3] is None:
+                after |= rest
+            fr.active = after
         elif kind in ("let", "var"):
             if kind == "var":
                 raise NotImplementedError("SIMT executor: function-scope `var` (none of the step shaders has one)")
@@ -235,6 +265,19 @@ class _Lanes:
         if name in self.d.foreign:
             raise self.d.conflict(name)
         k = max(0, min(len(data), self.hi) - self.lo)  # lanes whose own element exists: the rest is dropped
+        if isinstance(val, Vec3):
+            if data.ndim != 2 or data.shape[1] != 3:
+                raise TypeError(f"WGSL: storing a vec3 into `{name}`")
+            for c, comp in enumerate(val.c):
+                if _is_abstract(comp):
+                    comp = data.dtype.type(comp)
+                if isinstance(comp, np.ndarray):
+                    if comp.dtype != data.dtype:
+                        raise TypeError(f"WGSL: storing vec3<{comp.dtype}> into `{name}`")
+                    np.copyto(data[self.lo:self.lo + k, c], comp[:k], where=active[:k])
+                else:
+                    data[self.lo:self.lo + k, c][active[:k]] = comp
+            return
         if _is_abstract(val):
             val = data.dtype.type(val)
         if isinstance(val, np.ndarray):
@@ -287,6 +330,12 @@ class _Lanes:
 
     @staticmethod
     def _binop(op, a, b):
+        if isinstance(a, Vec3) or isinstance(b, Vec3):  # component-wise, scalars are splat
+            ac = a.c if isinstance(a, Vec3) else [a] * 3
+            bc = b.c if isinstance(b, Vec3) else [b] * 3
+            if op not in "+-*/":
+                raise NotImplementedError(f"vec3 operator {op}")
+            return Vec3([_Lanes._binop(op, x, y) for x, y in zip(ac, bc)])
         a, b = _unify(a, b)
         if not _is_abstract(a):
             ta = a.dtype if isinstance(a, np.ndarray) else np.dtype(type(a))
@@ -340,6 +389,16 @@ class _Lanes:
             inner = _Frame([self.d.env, scope], fr.active.copy())
             self._block(fn["body"], inner)
             return inner.ret
+        if name == "vec3":
+            return Vec3(args * 3 if len(args) == 1 else args)
+        if name == "i32":
+            a = args[0]
+            if isinstance(a, np.ndarray) and a.dtype.kind == "f":  # truncate toward zero, saturate, NaN -> 0
+                t = np.clip(np.trunc(np.where(np.isnan(a), 0, a)), -2147483648.0, 2147483520.0)
+                return t.astype(i32)
+            if isinstance(a, np.ndarray):
+                return a.astype(i32)
+            return i32(int(a))
         if name == "f32":
             a = args[0]
             return a.astype(f32) if isinstance(a, np.ndarray) else f32(a)
@@ -369,10 +428,8 @@ class _Lanes:
 
 class WgslLBMVec(WgslLBM):
     """WgslLBM (the reference's host-side dispatch order, lbm.rs) with the step and summary shaders executed by the
-    SIMT executor; barrier_draw.wgsl (a scatter) and the vec3 colour maps keep the scalar interpreter."""
+    SIMT executor, colour maps included; only barrier_draw.wgsl (a scatter) keeps the scalar interpreter."""
 
-    VECTOR = ("pre_corner", "pre_cardinal", "col_cardinal", "col_corner", "ne_sw", "nw_se", "n_s", "e_w",
-              "ux", "uy", "rho", "speed", "curl")
 
     def __init__(self, omega, x, y, inflow_ux=0.1, root=None, threads=1):
         from . import wgsl_interp
@@ -384,10 +441,16 @@ class WgslLBMVec(WgslLBM):
                "ne_sw": "stream/ne_sw_stream.wgsl", "nw_se": "stream/se_nw_stream.wgsl",
                "n_s": "stream/n_s_stream.wgsl", "e_w": "stream/e_w_stream.wgsl", "ux": "summary_stats/ux.wgsl",
                "uy": "summary_stats/uy.wgsl", "rho": "summary_stats/rho.wgsl", "speed": "summary_stats/speed.wgsl",
-               "curl": "summary_stats/curl.wgsl"}
+               "curl": "summary_stats/curl.wgsl", "inferno": "color_map/inferno.wgsl",
+               "viridis": "color_map/viridis.wgsl", "jet": "color_map/jet.wgsl"}
         self.vsh = {k: VecShader(os.path.join(root, v)) for k, v in rel.items()}
         self.threads = int(threads)
         self.pool = ThreadPoolExecutor(self.threads) if self.threads > 1 else None
+
+    def color_map(self, name=None):
+        name = name or self.color_map_name
+        self.vsh[name].dispatch(self.work_groups, {(0, 0): self.colors, (1, 0): self.output, (2, 0): self.barrier,
+                                                   (3, 0): u32(self.n)}, threads=self.threads, pool=self.pool)
 
     def _run(self, name, bindings):
         if name in self.vsh:

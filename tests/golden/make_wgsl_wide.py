@@ -28,8 +28,14 @@ def run(name):
     t = time.time()
     sim = WgslLBMVec(omega, w, h, inflow_ux=u0, threads=THREADS if w * h >= (1 << 22) else 1)
     shots = wgsl_cases.replay(script, sim, lambda s: wgsl_cases.digest_snapshot(s.state()))
+    extra = {}
+    if name == wgsl_cases.COLOR_CASE:
+        for stat in range(5):
+            sim.compute_summary(stat)
+            for cmap in range(3):
+                extra[f"{name}/colors/{stat}/{cmap}"] = np.bytes_(wgsl_cases.digest_array(sim.colors_of(cmap)))
     print(f"{name}: {len(shots)} snapshots, {time.time() - t:.0f} s", flush=True)
-    return name, shots
+    return name, shots, extra
 
 
 def main():
@@ -38,7 +44,8 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "wgsl_wide.npz")
     arrays = dict(np.load(out)) if sys.argv[1:] and os.path.exists(out) else {}
     with ProcessPoolExecutor(min(len(names), os.cpu_count() or 1)) as ex:
-        for name, shots in ex.map(run, names):
+        for name, shots, extra in ex.map(run, names):
+            arrays.update(extra)
             arrays[f"{name}/count"] = np.int64(len(shots))
             for i, d in enumerate(shots):
                 for k, v in d.items():

@@ -33,6 +33,8 @@ class MockLBM:
         pts = barrier_shapes.line_points(p1, p2, self.x, self.y, erase=erase)
         a = np.array([[px + py * self.x, 0 if erase else 1] for px, py, *_ in pts], np.uint32)
         self.o.draw_points(a)
+    def color_map(self, cmap): self._rgb = self.o.color_map(cmap)
+    def read_colors(self): return self._rgb
     def draw_line(self, p1, p2): self._line(p1, p2, False)
     def erase_line(self, p1, p2): self._line(p1, p2, True)
     def close(self): self.o.close()

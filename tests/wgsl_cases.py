@@ -101,6 +101,7 @@ def _porous_strip(w, h):
 
 
 SLOW_CASE = "box_4096x4096_1000steps"
+COLOR_CASE = "colormaps_700x300"
 
 
 def wide_cases():
@@ -114,10 +115,22 @@ def wide_cases():
     # SURVEY.md 8d config 2 as specified: the 4096^2 closed box for 1,000 steps (the oracle needs ~3 minutes for it,
     # so its CPU test only runs with BLBM_SLOW_ORACLE=1; the GPU test always runs)
     out[SLOW_CASE] = (1.25, 4096, 4096, 0.1, _box(4096, 4096, steps=(100, 200, 700)))
+    # row N3: after the script, every summary statistic through every colour map (digests under <name>/colors/..)
+    out[COLOR_CASE] = (1.0 / (3 * 0.02 + 0.5), 700, 300, 0.1,
+                       [("draw", disc_pairs(700, 175, 150, 20).astype(np.uint32)), ("iterate", 400), ("compare",)])
     for w, h, steps in ((300, 170, 40), (1001, 37, 30), (4100, 5, 12)):
         rng = np.random.default_rng(9000 * w + h)
         out[f"random_{w}x{h}"] = (1.0 / (3 * 0.02 + 0.5), w, h, 0.1, random_script(rng, w, h, max_steps=steps))
     return out
+
+
+def digest_array(a):
+    import hashlib
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        a = a.copy()
+        a[np.isnan(a)] = np.float32(np.nan)
+    return hashlib.sha256(a.tobytes()).hexdigest()
 
 
 def digest_snapshot(st):
