@@ -252,13 +252,9 @@ class LBM:
     def draw_shape(self, shape):
         """shape: anything with get_points() -> iterable of (x, y, bool), like `trait Shape`
         (barrier_shapes/mod.rs:11-19); flattened as get_points_vector does (merge_shapes.rs:12-22)."""
-        pts = list(shape.get_points())
-        if not pts:
+        a = points_vector(shape.get_points(), self.x)
+        if not len(a):
             return  # the reference's callers guard with is_empty() (lib.rs:147)
-        a = np.empty((len(pts), 2), np.uint64)
-        for q, (px, py, on) in enumerate(pts):
-            a[q, 0] = int(px) + int(py) * self.x
-            a[q, 1] = 1 if on else 0
         self.draw_points(a)
 
     def reset_barrier(self):
@@ -389,6 +385,17 @@ class LBM:
 
     def device_bytes(self):
         return int(self._L.blbm_get_device_bytes(self._h))
+
+
+def points_vector(points, xdim):
+    """get_points_vector (merge_shapes.rs:12-22): (x, y, bool) -> [x + y*xdim, 1 | 0] pairs, the array
+    draw_barrier_updates uploads for barrier_draw.wgsl (lbm.rs:1341-1343) and blbm_draw_points takes."""
+    pts = list(points)
+    a = np.empty((len(pts), 2), np.uint64)
+    for q, (px, py, on) in enumerate(pts):
+        a[q, 0] = int(px) + int(py) * int(xdim)
+        a[q, 1] = 1 if on else 0
+    return a
 
 
 def rasterize_line(p1, p2, xdim, ydim, erase=False):

@@ -299,6 +299,7 @@ class Instance:
         self.globals = list(module.globals)
         self.imports = imports or {}
         self.hooks = hooks or {}  # function index -> callable(instance, *args): replaces a function of the module
+        self.virtual_table = {}   # table index beyond the module's table -> callable(instance, *args) for call_indirect
         self.steps = 0
         self.max_steps = max_steps
         self.called = []
@@ -425,6 +426,15 @@ class Instance:
                 st += self._invoke(f, a)
             elif op == 0x11:
                 i = st.pop()
+                if i in self.virtual_table:  # a host-provided trait-object method (e.g. a fabricated Rust vtable)
+                    np_ = len(m.types[ins[1]][0])
+                    a = st[len(st) - np_:] if np_ else []
+                    if np_:
+                        del st[len(st) - np_:]
+                    r = self.virtual_table[i](self, *a)
+                    if m.types[ins[1]][1]:
+                        st.append(r)
+                    continue
                 if i >= len(m.table) or m.table[i] is None:
                     raise Trap("undefined table element")
                 f = m.table[i]

@@ -6,6 +6,9 @@
   * `LBM::single_cell` (lbm.rs:1502-1515, with `set_single_cell` :1482-1500 inlined) on a fabricated `LBM` value,
     its 18 `queue.write_buffer` calls intercepted: which population is set to 4.0 at which cell for every preset
     index, and what every other cell holds — row a-8;
+  * `LBM::draw_shape` (lbm.rs:1337-1343, with `get_points_vector`, merge_shapes.rs:12-22, inlined) on Curves holding
+    drawn and erased lines: the exact u32 pairs and the count word it uploads for barrier_draw.wgsl — the wire format
+    of row a-7, i.e. what blbm_draw_points must accept;
   * `Line::new` (barrier_shapes/line.rs:22-54) called directly, and `Line::new_erased` (line.rs:56-87, the 30-wide
     eraser) and `Line::new` again through `Curve::erase_segment` / `Curve::add_segment` (curve.rs:28-48): the
     point sets of thick lines, with the un-vendored `line_drawing 1.0.0` Bresenham as compiled into the binary —
@@ -33,7 +36,7 @@ from oracle.wasm_mini import Instance, Module, Trap  # noqa: E402
 
 WASM = "/root/reference/lbm-wgpu/pkg/lbm_wgpu_bg.wasm"
 F_SET_EQUIL, F_LINE_NEW, F_ERASE_SEGMENT, F_ADD_SEGMENT = 268, 249, 307, 308
-F_SINGLE_CELL, F_WRITE_BUFFER = 247, 591
+F_SINGLE_CELL, F_WRITE_BUFFER, F_DRAW_SHAPE = 247, 591, 267
 # struct LBM as laid out in this build (read off the code of LBM::single_cell): xdim, ydim, data_buffers {ptr, len};
 # a wgpu::Buffer is 88 bytes, the wgpu::Queue sits 128 bytes into Driver
 LBM_X, LBM_Y, LBM_BUFFERS_PTR, LBM_BUFFERS_LEN, SIZEOF_BUFFER, DRIVER_QUEUE = 1100, 1104, 1160, 1164, 88, 128
@@ -96,6 +99,11 @@ def check_fingerprints(m):
     assert [i[1] for i in code if i[0] == 0x10].count(F_SET_EQUIL) == 1
     assert [i[1] for i in code if i[0] == 0x10].count(F_WRITE_BUFFER) >= 18
     assert 0x40800000 in consts(F_SINGLE_CELL, 0x41)
+    # draw_shape(&mut self, &driver, &dyn Shape): one trait-object call (get_points), two uploads, reads self.x
+    code = m.decode(F_DRAW_SHAPE)[1]
+    assert m.type_of(F_DRAW_SHAPE) == ([I32] * 4, [])
+    assert [i[1] for i in code if i[0] == 0x10].count(F_WRITE_BUFFER) == 2
+    assert any(i[0] == 0x28 and i[1] == LBM_X for i in code) and code[[i[0] for i in code].index(0x11)][0] == 0x11
     # hashbrown's static empty control group, referenced where the functions create an empty HashSet
     empty = [c for c in consts(F_LINE_NEW, 0x41) if 1 << 20 <= c < 1 << 21 and
              any(off <= c < off + len(b) and b[c - off:c - off + 4] == b"\xff" * 4 for off, b in m.segments)]
@@ -180,6 +188,33 @@ class Reference:
         assert len(got) == 18 and all(len(v) == x * y for v in got.values()) and not inst.called
         return np.stack([np.stack([got[(b, k)] for k in range(9)]) for b in range(2)]).reshape(2, 9, y, x)
 
+    def draw_shape(self, erase, p1, p2, xdim, ydim):
+        """LBM::draw_shape(&mut self, &driver, &dyn Shape) (lbm.rs:1337-1343, get_points_vector of merge_shapes.rs
+        inlined) on a Curve holding the line p1 -> p2, through a fabricated `dyn Shape` vtable whose get_points is
+        served by the host; returns (the u32 array uploaded to draw_points, the word uploaded to draw_num, the
+        shape's points).  The function traps at its first wgpu call after the two uploads."""
+        got = []
+        inst = Instance(self.m, imports=self.stubs,
+                        hooks={F_WRITE_BUFFER: lambda i, q, b, ptr, n: got.append(
+                            np.frombuffer(i.read(ptr, n), dtype=np.uint32).copy())})
+        malloc = self.m.exports["__wbindgen_malloc"][1]
+        me, drv, cur, vt = (inst.call(malloc, n, 8) for n in (2048, 1024, 64, 32))
+        for a, n in ((me, 2048), (drv, 1024), (cur, 64)):
+            inst.mem[a:a + n] = bytes(n)
+        struct.pack_into("<QQIIIIIii", inst.mem, cur, 1, 2, 0, 0, 0, self.empty_group, 1, p1[0], p1[1])
+        inst.call(F_ERASE_SEGMENT if erase else F_ADD_SEGMENT, cur, p2[0] & 0xFFFFFFFF, p2[1] & 0xFFFFFFFF, xdim, ydim)
+        pts = self._read_set(inst, cur)
+        struct.pack_into("<I", inst.mem, me + LBM_X, xdim)
+        virt = 1 << 20  # a table index the module does not have: served by virtual_table
+        struct.pack_into("<IIII", inst.mem, vt, 0, 44, 8, virt)  # {drop, size, align, get_points}
+        inst.virtual_table[virt] = lambda i, this: this  # Curve::get_points(&self) -> &self.points (offset 0)
+        try:
+            inst.call(F_DRAW_SHAPE, me, drv, cur, vt)
+        except Trap:
+            pass  # queue.submit(None) through the zeroed Driver's `dyn Context`, after both uploads
+        assert len(got) == 2 and len(got[1]) == 1 and not inst.called
+        return got[0], int(got[1][0]), pts
+
     def line_new(self, p1, p2, xdim, ydim):
         inst, ret = self._instance()
         inst.call(F_LINE_NEW, ret, *(v & 0xFFFFFFFF for v in (p1[0], p1[1], p2[0], p2[1], xdim, ydim)))
@@ -204,6 +239,16 @@ def main():
         print(f"single_cell on {x}x{y}: 10 presets", flush=True)
     out["single_cell_sizes"] = np.array(SINGLE_CELL_SIZES, np.int64)
     cases = line_cases()
+    n_draw = 0
+    for i, (a, b, xd, yd) in enumerate(cases):
+        if xd == 64 and i % 4 == 0 and min(a + b) >= 0 and max(a[0], b[0]) < xd and max(a[1], b[1]) < yd:
+            for erase in (0, 1):
+                pairs, count, pts = ref.draw_shape(bool(erase), a, b, xd, yd)
+                out[f"draw/{i}/{erase}/pairs"] = pairs.reshape(-1, 2)
+                out[f"draw/{i}/{erase}/count"] = np.int64(count)
+                out[f"draw/{i}/{erase}/points"] = np.array(pts, np.int32).reshape(-1, 3)
+            n_draw += 1
+    print(f"draw_shape: {n_draw} lines, drawn and erased", flush=True)
     out["line_cases"] = np.array([[a[0], a[1], b[0], b[1], xd, yd] for a, b, xd, yd in cases], np.int64)
     for i, (a, b, xd, yd) in enumerate(cases):
         pts = ref.line_new(a, b, xd, yd)

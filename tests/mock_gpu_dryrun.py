@@ -53,6 +53,7 @@ g = np.load(tw.GOLDEN)
 tw.test_cuda_initial_state_equals_the_reference_binarys_set_equil(g); print("ok set_equil")
 tw.test_cuda_single_cell_equals_what_the_reference_binary_uploads(g); print("ok single_cell")
 tw.test_cuda_draw_line_paints_the_reference_binarys_cells(g); print("ok draw_line")
+tw.test_cuda_draw_points_accepts_what_the_reference_binary_uploads(g); print("ok draw_points wire format")
 c1 = np.load(tg.CONFIG1); wide = np.load(tg.WIDE); gold = np.load(tg.GOLDEN)
 skip = {"box_4096x4096", "box_4096x4096_1000steps"}
 for name in sorted(tg.WIDE_CASES):

@@ -4,6 +4,8 @@ tests/golden/wasm_golden.npz holds the results of executing functions of the ref
 (lbm-wgpu/pkg/lbm_wgpu_bg.wasm, run in oracle/wasm_mini.py by tests/golden/make_wasm_golden.py):
   * `set_equil` (lbm.rs:611-643) -> the nine initial populations for eight inflow speeds   
   * `LBM::single_cell` (lbm.rs:1482-1515) -> the 18 arrays it uploads, for every preset index on four lattice sizes (row a-8)
+  * `LBM::draw_shape` (lbm.rs:1337-1343 + merge_shapes.rs:12-22) -> the u32 pairs and the count word it uploads for
+    barrier_draw.wgsl, for drawn and erased lines: the wire format blbm_draw_points takes                 (row a-7)
   * `Line::new` / `Line::new_erased` (barrier_shapes/line.rs:22-87, with the un-vendored line_drawing 1.0.0
     Bresenham as compiled in) -> the cells of 99 thick lines on two lattice sizes           (row N2)
 Here the oracle's restatements, the product's host-side rasteriser (libblbm.so: blbm_rasterize_line is pure host
@@ -111,6 +113,31 @@ def test_host_rasteriser_equals_the_reference_binarys_lines(golden):
     assert n_new >= 90 and n_erased >= 50 and n_err == 3
 
 
+def draw_cases(golden):
+    for key in sorted(k for k in golden.files if k.startswith("draw/") and k.endswith("/pairs")):
+        _, i, erase, _ = key.split("/")
+        x1, y1, x2, y2, xd, yd = golden["line_cases"][int(i)].tolist()
+        yield (x1, y1), (x2, y2), xd, yd, int(erase), golden[key], int(golden[f"draw/{i}/{erase}/count"]), \
+            golden[f"draw/{i}/{erase}/points"]
+
+
+def test_paint_wire_format_equals_what_the_reference_binary_uploads(golden):
+    """draw_shape as compiled: the array handed to barrier_draw.wgsl is [x + y*W, 1|0] per point of the shape (hash
+    order), and the count word is 2n - 1 (`points.len() as u32 - 1` on the flattened vector, lbm.rs:1343).  The
+    product's host-side flattening (lbm_b200.lbm.points_vector, used by LBM.draw_shape) and the host rasteriser
+    produce the same set of pairs."""
+    from lbm_b200.lbm import points_vector, rasterize_line
+    n = 0
+    for p1, p2, xd, yd, erase, pairs, count, pts in draw_cases(golden):
+        want = sorted(map(tuple, pairs.tolist()))
+        assert count == 2 * len(pairs) - 1 and len(pairs) == len(pts)
+        assert sorted(map(tuple, points_vector([(x, y, bool(f)) for x, y, f in pts.tolist()], xd).tolist())) == want
+        ours = rasterize_line(p1, p2, xd, yd, erase=bool(erase))
+        assert sorted((x + y * xd, 0 if erase else 1) for x, y in ours.tolist()) == want
+        n += 1
+    assert n >= 16
+
+
 @needs_reference
 def test_fixture_comes_from_the_binary_in_the_reference_tree_and_reruns_live(golden):
     from tests.golden.make_wasm_golden import Reference
@@ -189,6 +216,24 @@ def test_cuda_single_cell_equals_what_the_reference_binary_uploads(golden):
                 assert (bits(lbm.read_population(k, b)) == bits(want[b, k])).all(), (x, y, index, b, k)
         assert lbm.get_compute_num() == 0
         lbm.close()
+
+
+@pytest.mark.gpu
+def test_cuda_draw_points_accepts_what_the_reference_binary_uploads(golden):
+    """the drop-in check for row a-7: the very arrays the reference's draw_shape uploads, handed to blbm_draw_points"""
+    from lbm_b200 import LBM
+    n = 0
+    for p1, p2, xd, yd, erase, pairs, count, pts in draw_cases(golden):
+        lbm = LBM(1.0, xd, yd)
+        if erase:
+            lbm.draw_points(np.stack([pairs[:, 0], np.ones_like(pairs[:, 0])], 1))  # something to erase
+        expect = lbm.read_barrier().copy()
+        lbm.draw_points(pairs.astype(np.uint32))
+        expect[pts[:, 1], pts[:, 0]] = 0 if erase else 1
+        assert np.array_equal(lbm.read_barrier(), expect), (p1, p2, erase)
+        lbm.close()
+        n += 1
+    assert n >= 16
 
 
 @pytest.mark.gpu
