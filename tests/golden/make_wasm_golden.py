@@ -65,6 +65,20 @@ def line_cases():
     return c
 
 
+def curve_chains():
+    """(ops, xdim, ydim) with ops = [(erase, x, y), ...]: strokes as the click handler builds them (lib.rs:130-160)"""
+    rng = np.random.default_rng(77)
+    chains = [([(0, 5, 5)], 64, 32), ([(1, 9, 9)], 64, 32),
+              ([(0, 3, 4), (0, 20, 11), (0, 25, 30), (0, 60, 2)], 64, 32),
+              ([(0, 10, 10), (0, 40, 10), (1, 40, 25), (0, 12, 25)], 64, 32),
+              ([(1, 30, 16), (1, 34, 16)], 64, 32)]
+    for _ in range(4):
+        n = int(rng.integers(3, 7))
+        chains.append(([(int(rng.integers(0, 4) == 0), int(rng.integers(0, 200)), int(rng.integers(0, 120)))
+                        for _ in range(n)], 200, 120))
+    return chains
+
+
 def check_fingerprints(m):
     def consts(f, op):
         return {i[1] for i in m.decode(f)[1] if i[0] == op}
@@ -215,6 +229,16 @@ class Reference:
         assert len(got) == 2 and len(got[1]) == 1 and not inst.called
         return got[0], int(got[1][0]), pts
 
+    def curve_chain(self, ops, xdim, ydim):
+        """Curve::new() followed by add_segment / erase_segment calls on the same value (curve.rs:20-48):
+        ops = [(erase, x, y), ...]; returns the curve's points (a cell may be present with both flags)"""
+        inst, cur = self._instance()
+        struct.pack_into("<QQIIIIIii", inst.mem, cur, 1, 2, 0, 0, 0, self.empty_group, 0, 0, 0)  # last_point: None
+        for erase, x, y in ops:
+            inst.call(F_ERASE_SEGMENT if erase else F_ADD_SEGMENT, cur, x & 0xFFFFFFFF, y & 0xFFFFFFFF, xdim, ydim)
+            assert inst.u32(cur + 32) == 1 and (inst.i32(cur + 36), inst.i32(cur + 40)) == (x, y)
+        return self._read_set(inst, cur)
+
     def line_new(self, p1, p2, xdim, ydim):
         inst, ret = self._instance()
         inst.call(F_LINE_NEW, ret, *(v & 0xFFFFFFFF for v in (p1[0], p1[1], p2[0], p2[1], xdim, ydim)))
@@ -261,6 +285,11 @@ def main():
         if i % 3 == 0 or xd == 64:  # the 30-wide eraser is slow to interpret: a subset of the cases
             out[f"line/{i}/erased"] = np.array(ref.curve_segment(True, a, b, xd, yd), np.int32).reshape(-1, 3)
         print(f"case {i}: {a} -> {b} on {xd}x{yd}: {len(pts)} cells", flush=True)
+    for j, (ops, xd, yd) in enumerate(curve_chains()):
+        out[f"curve/{j}/ops"] = np.array(ops, np.int64)
+        out[f"curve/{j}/dims"] = np.array([xd, yd], np.int64)
+        out[f"curve/{j}/points"] = np.array(ref.curve_chain(ops, xd, yd), np.int32).reshape(-1, 3)
+        print(f"curve chain {j}: {len(ops)} segments -> {len(out[f'curve/{j}/points'])} points", flush=True)
     path = os.path.join(HERE, "wasm_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

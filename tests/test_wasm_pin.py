@@ -6,6 +6,7 @@ tests/golden/wasm_golden.npz holds the results of executing functions of the ref
   * `LBM::single_cell` (lbm.rs:1482-1515) -> the 18 arrays it uploads, for every preset index on four lattice sizes (row a-8)
   * `LBM::draw_shape` (lbm.rs:1337-1343 + merge_shapes.rs:12-22) -> the u32 pairs and the count word it uploads for
     barrier_draw.wgsl, for drawn and erased lines: the wire format blbm_draw_points takes                 (row a-7)
+  * `Curve::add_segment` / `erase_segment` chains (curve.rs:20-48) -> the points of whole strokes, against the C++ mirror
   * `Line::new` / `Line::new_erased` (barrier_shapes/line.rs:22-87, with the un-vendored line_drawing 1.0.0
     Bresenham as compiled in) -> the cells of 99 thick lines on two lattice sizes           (row N2)
 Here the oracle's restatements, the product's host-side rasteriser (libblbm.so: blbm_rasterize_line is pure host
@@ -136,6 +137,29 @@ def test_paint_wire_format_equals_what_the_reference_binary_uploads(golden):
         assert sorted((x + y * xd, 0 if erase else 1) for x, y in ours.tolist()) == want
         n += 1
     assert n >= 16
+
+
+def test_cpp_curve_equals_the_reference_binarys_curve(golden, tmp_path):
+    """include/blbm.hpp's Curve (add_segment / erase_segment chains, curve.rs:28-48) compiled and run on the host
+    against the same strokes executed in the reference's binary; a cell may carry both flags, as in the reference"""
+    import subprocess
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "lbm_b200")
+    exe = str(tmp_path / "curve_chain")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(root, "include"),
+                        os.path.join(HERE, "cpp", "curve_chain.cpp"), "-o", exe, "-L", libdir, "-lblbm",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n = 0
+    while f"curve/{n}/ops" in golden.files:
+        ops, (xd, yd), want = golden[f"curve/{n}/ops"].tolist(), golden[f"curve/{n}/dims"].tolist(), golden[f"curve/{n}/points"]
+        r = subprocess.run([exe, str(xd), str(yd)] + [str(v) for op in ops for v in op], capture_output=True, text=True,
+                           timeout=60)
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = sorted(tuple(int(v) for v in line.split()) for line in r.stdout.splitlines())
+        assert got == sorted(map(tuple, want.tolist())), f"curve chain {n}: {ops}"
+        n += 1
+    assert n >= 9
 
 
 @needs_reference
