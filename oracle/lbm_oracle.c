@@ -5,17 +5,24 @@
  * call this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and only as the checker / the timed CPU arm.
  *
- * PARITY STATUS: the reference (PPLUSCHT/LBM) ships no tests, golden vectors or read-back path, and
- * cannot be built or run here (Rust -> wasm32 + browser WebGPU; no cargo / Vulkan / lavapipe in the image),
- * so no output of an actual wgpu execution exists: in that strict sense parity is UNPINNED.  What pins this
- * oracle instead: (a) the reference's own WGSL shader text, parsed and executed invocation by invocation by
- * oracle/wgsl_interp.py, produced tests/golden/wgsl_golden.npz (random API scripts, config-1 miniatures,
- * porous mask, single_cell presets, paints on every special cell class, every summary statistic and colour
- * map); this file must reproduce those buffers bit for bit (tests/test_wgsl_pin.py), so the arithmetic,
- * association, guards and index helpers are pinned to the reference's source, with only the host-side
- * dispatch order restated from lbm.rs; (b) an independent numpy restatement (oracle/lbm_numpy.py) that must
- * agree bit for bit; (c) analytic known-answer tests.  Not pinned by anything: what a particular WebGPU
- * backend does where WGSL leaves room (FMA contraction, out-of-range access) -- see the semantics below.
+ * PARITY STATUS: the reference (PPLUSCHT/LBM) ships no tests or golden vectors and has no read-back path; its WebGPU
+ * half cannot run here (Rust -> wasm32 + browser WebGPU; no cargo / Vulkan / lavapipe in the image), so no output of
+ * an actual wgpu execution exists.  What pins this oracle:
+ *   (a) OUTPUTS OF THE REFERENCE ITSELF for its host-side rows: oracle/wasm_mini.py executes functions of the
+ *       reference's shipped binary (lbm-wgpu/pkg/lbm_wgpu_bg.wasm): set_equil, LBM::single_cell, LBM::draw_shape,
+ *       Line::new, Line::new_erased, Curve::add/erase_segment -> tests/golden/wasm_golden.npz; this file's initial
+ *       populations and single_cell state must equal them bit for bit (tests/test_wasm_pin.py);
+ *   (b) the reference's own WGSL shader text (verified to be embedded byte for byte in that binary), executed
+ *       invocation by invocation by oracle/wgsl_interp.py (tests/golden/wgsl_golden.npz: random API scripts, config-1
+ *       miniatures, porous mask, single_cell presets, paints on every special cell class, every summary statistic
+ *       and colour map) and, all invocations at once, by oracle/wgsl_simt.py at the reference's own sizes
+ *       (wgsl_config1.npz: BASELINE configs[0] in full, 512 x 256 for 10,000 steps; wgsl_wide.npz: configs[1] at
+ *       4096^2 for 1,000 steps, a 16384-wide porous strip, colour maps at 700 x 300); this file must reproduce
+ *       every buffer / digest bit for bit (tests/test_wgsl_pin.py), so arithmetic, association, guards and index
+ *       helpers are pinned to the reference's source, with only the host-side dispatch order restated from lbm.rs;
+ *   (c) an independent numpy restatement (oracle/lbm_numpy.py) that must agree bit for bit; (d) analytic KATs.
+ * Still UNPINNED: what a particular WebGPU backend does where WGSL leaves room (FMA contraction, out-of-range
+ * access) -- see the semantics below.
  *
  * The reference's structure is preserved on purpose: 8 passes per step over 2x9 fp32 SoA arrays,
  * three moment arrays and a u32 barrier mask, every intermediate going through fp32 memory exactly
