@@ -165,7 +165,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.lbm_oracle import Oracle, threads
+    from oracle.lbm_oracle import Oracle, threads, use_all_cores
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        use_all_cores()  # torchrun exported OMP_NUM_THREADS=1; the other ranks have exited, rank 0 owns the host
     w, rows_gpu, omega, u0, kind = WORKLOADS[args.workload]
     # size the strip so that (steps + warmup) steps take about two minutes
     calib_rows = max(16, (4 << 20) // w)

@@ -444,6 +444,17 @@ float *lbm_oracle_rho(lbm_oracle *o) { return o->rho; }
 float *lbm_oracle_output(lbm_oracle *o) { return o->out; }
 uint64_t lbm_oracle_compute_num(const lbm_oracle *o) { return o->step; }
 float lbm_oracle_omega(const lbm_oracle *o) { return o->omega; }
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU arm of bench.py runs on rank 0 alone and
+   asks for all host cores explicitly */
+void lbm_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int lbm_oracle_threads(void)
 {
 #ifdef _OPENMP

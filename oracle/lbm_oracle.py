@@ -60,6 +60,7 @@ def lib():
         L.lbm_oracle_compute_num.restype = C.c_uint64
         L.lbm_oracle_compute_num.argtypes = [P]
         L.lbm_oracle_threads.restype = C.c_int
+        L.lbm_oracle_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -72,6 +73,17 @@ def set_equil(ux, uy, rho):
 
 def threads():
     return lib().lbm_oracle_threads()
+
+
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on (torchrun sets OMP_NUM_THREADS=1 for every rank; the
+    timed CPU arm runs on rank 0 alone).  Returns the thread count in effect."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().lbm_oracle_set_threads(n)
+    return threads()
 
 
 class Oracle:

@@ -236,3 +236,16 @@ def test_color_maps_match_numpy_and_known_colours(cmap):
     assert tuple(c[5, 5]) == tuple(np.float32(mid))
     assert tuple(c[5, 6]) == tuple(np.float32(top))
     assert tuple(c[5, 7]) == tuple(np.float32(bot))
+
+
+def test_cpu_arm_can_claim_all_cores_under_torchrun(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; bench.py --impl reference (rank 0 alone) must still time the
+    oracle on all host cores"""
+    import os
+    from oracle import lbm_oracle
+    before = lbm_oracle.threads()
+    lbm_oracle.lib().lbm_oracle_set_threads(1)
+    assert lbm_oracle.threads() == 1
+    n = lbm_oracle.use_all_cores()
+    assert n == len(os.sched_getaffinity(0)) >= 1
+    lbm_oracle.lib().lbm_oracle_set_threads(before)
