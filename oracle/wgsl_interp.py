@@ -566,30 +566,34 @@ class WgslLBM:
     """`pub struct LBM` (lbm.rs:32-98) with every compute pass executed by interpreting the reference's WGSL.
     Same method names as the C oracle's Python wrapper (oracle/lbm_oracle.py) where they overlap."""
 
+    # lbm.rs:822-900, 969: which shader file each pipeline is built from
+    SHADERS = {
+        "pre_corner": "pre_collision/corner_pre_collision.wgsl",
+        "pre_cardinal": "pre_collision/cardinal_pre_collision.wgsl",
+        "col_cardinal": "collision/cardinal_collision.wgsl",
+        "col_corner": "collision/corner_collision.wgsl",
+        "ne_sw": "stream/ne_sw_stream.wgsl",
+        "nw_se": "stream/se_nw_stream.wgsl",
+        "n_s": "stream/n_s_stream.wgsl",
+        "e_w": "stream/e_w_stream.wgsl",
+        "ux": "summary_stats/ux.wgsl",
+        "uy": "summary_stats/uy.wgsl",
+        "rho": "summary_stats/rho.wgsl",
+        "speed": "summary_stats/speed.wgsl",
+        "curl": "summary_stats/curl.wgsl",
+        "draw": "update_barrier/barrier_draw.wgsl",
+        "inferno": "color_map/inferno.wgsl",
+        "viridis": "color_map/viridis.wgsl",
+        "jet": "color_map/jet.wgsl",
+    }
+
+    def _load_shaders(self, root):
+        self.sh = {name: Shader(os.path.join(root, rel)) for name, rel in self.SHADERS.items()}
+
     def __init__(self, omega, x, y, inflow_ux=0.1, root=SHADER_ROOT):
         self.x, self.y = int(x), int(y)
         self.n = self.x * self.y
-        sh = lambda rel: Shader(os.path.join(root, rel))  # noqa: E731
-        # lbm.rs:822-900, 969
-        self.sh = {
-            "pre_corner": sh("pre_collision/corner_pre_collision.wgsl"),
-            "pre_cardinal": sh("pre_collision/cardinal_pre_collision.wgsl"),
-            "col_cardinal": sh("collision/cardinal_collision.wgsl"),
-            "col_corner": sh("collision/corner_collision.wgsl"),
-            "ne_sw": sh("stream/ne_sw_stream.wgsl"),
-            "nw_se": sh("stream/se_nw_stream.wgsl"),
-            "n_s": sh("stream/n_s_stream.wgsl"),
-            "e_w": sh("stream/e_w_stream.wgsl"),
-            "ux": sh("summary_stats/ux.wgsl"),
-            "uy": sh("summary_stats/uy.wgsl"),
-            "rho": sh("summary_stats/rho.wgsl"),
-            "speed": sh("summary_stats/speed.wgsl"),
-            "curl": sh("summary_stats/curl.wgsl"),
-            "draw": sh("update_barrier/barrier_draw.wgsl"),
-            "inferno": sh("color_map/inferno.wgsl"),
-            "viridis": sh("color_map/viridis.wgsl"),
-            "jet": sh("color_map/jet.wgsl"),
-        }
+        self._load_shaders(root)
         self.omega = f32(omega)
         # lbm.rs:739-744: both buffer sets from the same initial data
         init = self.set_equil(f32(inflow_ux), f32(0.0), f32(1.0))

@@ -9,6 +9,10 @@
   * `LBM::draw_shape` (lbm.rs:1337-1343, with `get_points_vector`, merge_shapes.rs:12-22, inlined) on Curves holding
     drawn and erased lines: the exact u32 pairs and the count word it uploads for barrier_draw.wgsl — the wire format
     of row a-7, i.e. what blbm_draw_points must accept;
+  * `LBM::iterate` (lbm.rs:1065-1074 with compute_step, collide, stream, calculate_summary, color_map inlined) against
+    a mock of wgpu's `dyn DynContext`: the complete command stream — encoders, the eight labelled compute passes per
+    step with their pipeline and bind-group fields, which bind groups alternate with compute_step % 2, the dispatch
+    size field, the summary and colour-map passes — i.e. the host-side dispatch order of rows a-3 .. a-6;
   * `Line::new` (barrier_shapes/line.rs:22-54) called directly, and `Line::new_erased` (line.rs:56-87, the 30-wide
     eraser) and `Line::new` again through `Curve::erase_segment` / `Curve::add_segment` (curve.rs:28-48): the
     point sets of thick lines, with the un-vendored `line_drawing 1.0.0` Bresenham as compiled into the binary —
@@ -41,6 +45,13 @@ F_SINGLE_CELL, F_WRITE_BUFFER, F_DRAW_SHAPE = 247, 591, 267
 # a wgpu::Buffer is 88 bytes, the wgpu::Queue sits 128 bytes into Driver
 LBM_X, LBM_Y, LBM_BUFFERS_PTR, LBM_BUFFERS_LEN, SIZEOF_BUFFER, DRIVER_QUEUE = 1100, 1104, 1160, 1164, 88, 128
 SINGLE_CELL_SIZES = ((16, 12), (64, 32), (30, 17), (9, 7))
+# LBM::iterate against a mock of wgpu's `dyn DynContext`: vtable slots of this build, identified on draw_shape (whose
+# call sequence is known from lbm.rs:1341-1356) — and more LBM fields, found by perturbing them
+F_ITERATE = 246
+SLOT = {"queue_write_buffer": 85, "queue_submit": 91, "device_create_command_encoder": 37, "begin_compute_pass": 72,
+        "end_compute_pass": 73, "encoder_finish": 76, "set_pipeline": 96, "set_bind_group": 97,
+        "dispatch_workgroups": 105}
+LBM_COMPUTE_STEP, LBM_WORK_GROUP_SIZE, LBM_STAT_CMAP, DRIVER_DEVICE = 1088, 1096, 1168, 104
 I32, F32 = 0x7F, 0x7D
 
 INFLOWS = (0.1, 0.05, 0.0, 0.07, 0.03, 0.3, -0.1, 0.2)
@@ -239,6 +250,87 @@ class Reference:
             assert inst.u32(cur + 32) == 1 and (inst.i32(cur + 36), inst.i32(cur + 40)) == (x, y)
         return self._read_set(inst, cur)
 
+    def iterate_trace(self, n, compute_step=0, stat=0, cmap=2):
+        """LBM::iterate(&mut self, &driver, n) (lbm.rs:1065-1074: n x (collide; stream; compute_step += 1), then
+        calculate_summary + color_map) executed against a MOCK of wgpu's `dyn DynContext`: every word of the
+        fabricated Driver points at one object that serves both as ArcInner and as vtable, whose method slots are
+        served by the host and logged.  Every word of the fabricated LBM points into an arena (64 bytes per word), so
+        a `&self.field` argument decodes to the field's offset and `&self.vec[i]` to (offset of the Vec, i).
+        Returns the command stream: ["encoder"], ["pass", label, pipeline field, [[slot, field, index | None], ..],
+        dispatch field], ["submit"], ...  The run ends when iterate reaches render() (the surface is not mocked)."""
+        inst = Instance(self.m, imports=self.stubs)
+        malloc = self.m.exports["__wbindgen_malloc"][1]
+        virt, nslot, rev = 1 << 20, 256, {v: k for k, v in SLOT.items()}
+        uni = inst.call(malloc, 4 * nslot, 8)  # as vtable: {drop, size, align = 8, slots..}; as ArcInner: data at +8
+        struct.pack_into("<III", inst.mem, uni, virt, 0, 8)
+        for k in range(3, nslot):
+            struct.pack_into("<I", inst.mem, uni + 4 * k, virt + k)
+        anyvt = inst.call(malloc, 16, 4)  # Box<dyn Any> of returned objects: zero-sized, no-op drop
+        struct.pack_into("<IIII", inst.mem, anyvt, virt + 250, 0, 1, virt + 251)
+        me, drv = inst.call(malloc, 4096, 8), inst.call(malloc, 1024, 8)
+        arena = inst.call(malloc, 1024 * 64 + 64, 64)
+        inst.mem[arena:arena + 1024 * 64] = bytes(1024 * 64)
+        for off in range(0, 4096, 4):
+            struct.pack_into("<I", inst.mem, me + off, arena + (off // 4) * 64)
+        for off in range(0, 1024, 4):
+            struct.pack_into("<I", inst.mem, drv + off, uni)
+        struct.pack_into("<II", inst.mem, me + LBM_X, 64, 32)
+        struct.pack_into("<I", inst.mem, me + LBM_COMPUTE_STEP, compute_step)
+        struct.pack_into("<I", inst.mem, me + LBM_STAT_CMAP, stat | (cmap << 8))
+        stream, cur, ids = [], None, [100]
+
+        def field(v):
+            if me <= v < me + 4096:
+                return [v - me, None]
+            assert arena <= v < arena + 1024 * 64, hex(v)
+            assert (v - arena) % 64 % 24 == 0  # a wgpu::BindGroup is 24 bytes in this build
+            return [(v - arena) // 64 * 4, (v - arena) % 64 // 24]
+
+        def method(k):
+            def h(i, *a):
+                nonlocal cur
+                name = rev.get(k)
+                if name in ("device_create_command_encoder", "begin_compute_pass", "encoder_finish", "queue_submit"):
+                    out = a[0]
+                    ids[0] += 1
+                    struct.pack_into("<QII", i.mem, out, ids[0], 8, anyvt)  # (ObjectId, Box<dyn Any>)
+                    if name == "device_create_command_encoder":
+                        assert a[2] == drv + DRIVER_DEVICE
+                        stream.append(["encoder"])
+                    elif name == "begin_compute_pass":
+                        p, ln = i.u32(a[-1]), i.u32(a[-1] + 4)  # ComputePassDescriptor { label: Option<&str> }
+                        cur = ["pass", i.read(p, ln).decode() if p else None, None, [], None]
+                    elif name == "queue_submit":
+                        assert a[2] == drv + DRIVER_QUEUE
+                        stream.append(["submit"])
+                    return None
+                if name == "set_pipeline":
+                    cur[2] = field(a[4])[0]
+                elif name == "set_bind_group":
+                    assert a[9] == 0  # no dynamic offsets
+                    cur[3].append([a[4]] + field(a[5]))
+                elif name == "dispatch_workgroups":
+                    assert a[5] == 1 and a[6] == 1
+                    cur[4] = field(a[4])[0]  # the VALUE of a self word = its arena slot: which field was read
+                elif name == "end_compute_pass":
+                    stream.append(cur)
+                    cur = None
+                elif k in (250, 251):
+                    pass
+                else:
+                    raise Trap(f"unmocked DynContext slot {k}")
+                return 0
+            return h
+
+        for k in range(nslot):
+            inst.virtual_table[virt + k] = method(k)
+        try:
+            inst.call(F_ITERATE, me, drv, n)
+        except Trap:
+            pass  # render(): surface_get_current_texture is not mocked
+        assert inst.u32(me + LBM_COMPUTE_STEP) == compute_step + n and not inst.called
+        return stream
+
     def line_new(self, p1, p2, xdim, ydim):
         inst, ret = self._instance()
         inst.call(F_LINE_NEW, ret, *(v & 0xFFFFFFFF for v in (p1[0], p1[1], p2[0], p2[1], xdim, ydim)))
@@ -290,6 +382,13 @@ def main():
         out[f"curve/{j}/dims"] = np.array([xd, yd], np.int64)
         out[f"curve/{j}/points"] = np.array(ref.curve_chain(ops, xd, yd), np.int32).reshape(-1, 3)
         print(f"curve chain {j}: {len(ops)} segments -> {len(out[f'curve/{j}/points'])} points", flush=True)
+    import json
+    out["iterate_trace/steps3_from0"] = np.bytes_(json.dumps(ref.iterate_trace(3, compute_step=0)))
+    out["iterate_trace/steps2_from7"] = np.bytes_(json.dumps(ref.iterate_trace(2, compute_step=7)))
+    for stat in range(5):
+        for cmap in range(3):
+            out[f"iterate_trace/frame_only/{stat}/{cmap}"] = np.bytes_(json.dumps(ref.iterate_trace(0, stat=stat, cmap=cmap)))
+    print("iterate: command streams recorded", flush=True)
     path = os.path.join(HERE, "wasm_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

@@ -6,6 +6,9 @@ tests/golden/wasm_golden.npz holds the results of executing functions of the ref
   * `LBM::single_cell` (lbm.rs:1482-1515) -> the 18 arrays it uploads, for every preset index on four lattice sizes (row a-8)
   * `LBM::draw_shape` (lbm.rs:1337-1343 + merge_shapes.rs:12-22) -> the u32 pairs and the count word it uploads for
     barrier_draw.wgsl, for drawn and erased lines: the wire format blbm_draw_points takes                 (row a-7)
+  * `LBM::iterate` (lbm.rs:1065-1074, everything below it inlined) against a mock of wgpu's `dyn DynContext` -> the
+    complete command stream: encoders, labelled compute passes, pipeline and bind-group fields, alternation with
+    compute_step % 2, summary and colour-map passes — the host-side dispatch order                  (rows a-3 .. a-6)
   * `Curve::add_segment` / `erase_segment` chains (curve.rs:20-48) -> the points of whole strokes, against the C++ mirror
   * `Line::new` / `Line::new_erased` (barrier_shapes/line.rs:22-87, with the un-vendored line_drawing 1.0.0
     Bresenham as compiled in) -> the cells of 99 thick lines on two lattice sizes           (row N2)
@@ -160,6 +163,113 @@ def test_cpp_curve_equals_the_reference_binarys_curve(golden, tmp_path):
         assert got == sorted(map(tuple, want.tolist())), f"curve chain {n}: {ops}"
         n += 1
     assert n >= 9
+
+
+# the labels the reference gives its compute passes (lbm.rs:1174-1252) <-> the shader each pipeline is built from
+PASS_OF_LABEL = {"Precollision-corner": "pre_corner", "Precollision-cardinal": "pre_cardinal",
+                 "Collision-corner": "col_corner", "Collision-cardinal": "col_cardinal", "Stream_e_w": "e_w",
+                 "Stream_n_s": "n_s", "Stream_nw_se": "nw_se", "Stream_ne_sw": "ne_sw"}
+
+
+def recorded_driver(n, compute_step, stat, cmap):
+    """the oracle-side host driver (oracle/wgsl_interp.py: WgslLBM — the dispatch order every golden vector of
+    tests/golden/wgsl_*.npz was produced with) run WITHOUT shaders, recording per dispatch what it binds to each
+    bind-group slot: [(shader name, {group: identity of what is bound there})]"""
+    from oracle.wgsl_interp import REST, WgslLBM
+
+    class Recorder(WgslLBM):
+        def _load_shaders(self, root):
+            self.sh = {}
+
+        def identity(self, group_bindings):
+            ids = set()
+            for b in group_bindings:
+                hit = None
+                for buf in (0, 1):
+                    for k in range(9):
+                        if b is self.data[buf][k]:
+                            hit = ("rest",) if k == REST else ("population", buf, k)
+                for nm in ("ux", "uy", "rho", "output", "barrier", "colors"):
+                    if b is getattr(self, nm):
+                        hit = (nm,)
+                if hit is None:
+                    hit = ("dims",) if isinstance(b, dict) else ("size",) if isinstance(b, np.uint32) else ("omega",)
+                ids.add(hit)
+            return frozenset(ids)
+
+        def _run(self, name, bindings):
+            groups = {}
+            for (g, _), b in sorted(bindings.items()):
+                groups.setdefault(g, []).append(b)
+            self.log.append((name, {g: self.identity(v) for g, v in groups.items()}))
+
+        def color_map(self, name=None):
+            self._run(name or self.color_map_name, {(0, 0): self.colors, (1, 0): self.output, (2, 0): self.barrier,
+                                                    (3, 0): np.uint32(self.n)})
+
+    sim = Recorder(1.0, 8, 4)
+    sim.log = []
+    sim.compute_step = compute_step
+    sim.set_summary(Recorder.STATS[stat])
+    sim.iterate(n)
+    sim.color_map(Recorder.CMAPS[cmap])
+    return sim.log
+
+
+def check_command_stream(stream, n, compute_step, stat, cmap):
+    """the reference binary's command stream against the recorded driver: same passes in the same order, and ONE
+    consistent correspondence between the binary's bind-group fields (with their compute_step % 2 element) and what
+    the driver binds — in both directions"""
+    log = recorded_driver(n, compute_step, stat, cmap)
+    passes = [r for r in stream if r[0] == "pass"]
+    assert len(passes) == len(log) == 8 * n + 2
+    # shape of the stream: per step two encoders (4 collide passes, 4 stream passes), then one for summary + colours
+    kinds = [r[0] for r in stream]
+    assert kinds[:(6 + 6) * n] == (["encoder"] + ["pass"] * 4 + ["submit"]) * (2 * n)
+    assert kinds[12 * n:12 * n + 4] == ["encoder", "pass", "pass", "submit"]
+    field_to_identity, identity_to_field, pipeline_of = {}, {}, {}
+    dispatch_fields = set()
+    for (_, label, pipeline, groups, dispatch), (name, bound) in zip(passes, log):
+        if label is not None:
+            assert PASS_OF_LABEL[label] == name, (label, name)
+        assert pipeline_of.setdefault(name, pipeline) == pipeline  # one pipeline per shader ...
+        assert [g for g, _, _ in groups] == sorted(bound)  # the same bind-group slots are populated
+        for g, fld, idx in groups:
+            key = (fld, idx)
+            assert field_to_identity.setdefault(key, bound[g]) == bound[g], (label, g, key)
+            assert identity_to_field.setdefault(bound[g], key) == key, (label, g, key)
+        dispatch_fields.add(dispatch)
+    assert len(set(pipeline_of.values())) == len(pipeline_of)  # ... and distinct shaders use distinct pipelines
+    assert len(dispatch_fields) == 1  # every pass dispatches self.work_group_size = ceil(x*y / 256) workgroups
+    return field_to_identity
+
+
+def test_dispatch_order_equals_the_reference_binarys_command_stream(golden):
+    """LBM::iterate of the reference's binary, run against a mock wgpu context, emits per step: one encoder with the
+    passes Precollision-corner, Precollision-cardinal, Collision-corner, Collision-cardinal, one with Stream_e_w,
+    Stream_n_s, Stream_nw_se, Stream_ne_sw, then (per call) the summary and colour-map passes.  The oracle-side
+    driver must issue the same passes in the same order with a consistent one-to-one correspondence between bind
+    groups: the population pairs alternate with compute_step % 2 (streams: source = step % 2, destination = the
+    other), density / size / dimensions / barrier / output groups do not, and the collision group that carries the
+    rest population is a single, parity-independent bind group (lbm.rs:775-778)."""
+    import json
+    m0 = check_command_stream(json.loads(golden["iterate_trace/steps3_from0"].item()), 3, 0, 0, 2)
+    m7 = check_command_stream(json.loads(golden["iterate_trace/steps2_from7"].item()), 2, 7, 0, 2)
+    assert m0 == m7  # the correspondence does not depend on where compute_step starts
+    rest_groups = [k for k, v in m0.items() if ("rest",) in v]
+    assert len(rest_groups) == 1 and rest_groups[0][1] is None  # one bind group, not indexed by parity
+    pair_groups = [k for k, v in m0.items() if any(i[0] == "population" for i in v)]
+    assert len(pair_groups) == 8 and all(idx in (0, 1) for _, idx in pair_groups)
+    for (fld, idx), ident in m0.items():
+        if idx is not None:  # element i of a Vec<BindGroup> holds the pair's arrays of data_buffers[i]
+            assert {i[1] for i in ident} == {idx}
+    pipelines = set()
+    for stat in range(5):
+        for cmap in range(3):
+            stream = json.loads(golden[f"iterate_trace/frame_only/{stat}/{cmap}"].item())
+            check_command_stream(stream, 0, 0, stat, cmap)
+            pipelines.add(tuple(r[2] for r in stream if r[0] == "pass"))
+    assert len(pipelines) == 15 and len({p[0] for p in pipelines}) == 5 and len({p[1] for p in pipelines}) == 3
 
 
 @needs_reference
