@@ -9,7 +9,7 @@
  * half cannot run here (Rust -> wasm32 + browser WebGPU; no cargo / Vulkan / lavapipe in the image), so no output of
  * an actual wgpu execution exists.  What pins this oracle:
  *   (a) OUTPUTS OF THE REFERENCE ITSELF for its host-side rows: oracle/wasm_mini.py executes functions of the
- *       reference's shipped binary (lbm-wgpu/pkg/lbm_wgpu_bg.wasm): set_equil, LBM::single_cell, LBM::draw_shape,
+ *       reference's shipped binary (lbm-wgpu/pkg/lbm_wgpu_bg.wasm): set_equil, LBM::single_cell, LBM::draw_shape, LBM::iterate,
  *       Line::new, Line::new_erased, Curve::add/erase_segment -> tests/golden/wasm_golden.npz; this file's initial
  *       populations and single_cell state must equal them bit for bit (tests/test_wasm_pin.py);
  *   (b) the reference's own WGSL shader text (verified to be embedded byte for byte in that binary), executed
@@ -19,7 +19,9 @@
  *       (wgsl_config1.npz: BASELINE configs[0] in full, 512 x 256 for 10,000 steps; wgsl_wide.npz: configs[1] at
  *       4096^2 for 1,000 steps, a 16384-wide porous strip, colour maps at 700 x 300); this file must reproduce
  *       every buffer / digest bit for bit (tests/test_wgsl_pin.py), so arithmetic, association, guards and index
- *       helpers are pinned to the reference's source, with only the host-side dispatch order restated from lbm.rs;
+ *       helpers are pinned to the reference's source; the host-side dispatch order is checked against the command
+ *       stream of the binary's own LBM::iterate run on a mock wgpu context (a); only the bind-group contents are
+ *       restated from lbm.rs;
  *   (c) an independent numpy restatement (oracle/lbm_numpy.py) that must agree bit for bit; (d) analytic KATs.
  * Still UNPINNED: what a particular WebGPU backend does where WGSL leaves room (FMA contraction, out-of-range
  * access) -- see the semantics below.
