@@ -250,14 +250,14 @@ class Reference:
             assert inst.u32(cur + 32) == 1 and (inst.i32(cur + 36), inst.i32(cur + 40)) == (x, y)
         return self._read_set(inst, cur)
 
-    def iterate_trace(self, n, compute_step=0, stat=0, cmap=2):
-        """LBM::iterate(&mut self, &driver, n) (lbm.rs:1065-1074: n x (collide; stream; compute_step += 1), then
-        calculate_summary + color_map) executed against a MOCK of wgpu's `dyn DynContext`: every word of the
-        fabricated Driver points at one object that serves both as ArcInner and as vtable, whose method slots are
-        served by the host and logged.  Every word of the fabricated LBM points into an arena (64 bytes per word), so
-        a `&self.field` argument decodes to the field's offset and `&self.vec[i]` to (offset of the Vec, i).
-        Returns the command stream: ["encoder"], ["pass", label, pipeline field, [[slot, field, index | None], ..],
-        dispatch field], ["submit"], ...  The run ends when iterate reaches render() (the surface is not mocked)."""
+    def _mock_wgpu(self):
+        """An instance with a fabricated Driver and LBM for running methods of the binary against a MOCK of wgpu's
+        `dyn DynContext`: every word of the Driver points at one object that serves both as ArcInner and as vtable,
+        whose method slots are served by the host and logged.  Every word of the LBM points into an arena (64 bytes
+        per word), so a `&self.field` argument decodes to the field's offset and `&self.vec[i]` to (offset of the
+        Vec, i).  Returns (instance, self pointer, driver pointer, command stream) — the stream fills as the code
+        runs: ["encoder"], ["write", field, bytes], ["pass", label, pipeline field, [[slot, field, index | None],
+        ..], dispatch (field offset, or the number itself if it is not a word of self)], ["submit"], ..."""
         inst = Instance(self.m, imports=self.stubs)
         malloc = self.m.exports["__wbindgen_malloc"][1]
         virt, nslot, rev = 1 << 20, 256, {v: k for k, v in SLOT.items()}
@@ -274,21 +274,18 @@ class Reference:
             struct.pack_into("<I", inst.mem, me + off, arena + (off // 4) * 64)
         for off in range(0, 1024, 4):
             struct.pack_into("<I", inst.mem, drv + off, uni)
-        struct.pack_into("<II", inst.mem, me + LBM_X, 64, 32)
-        struct.pack_into("<I", inst.mem, me + LBM_COMPUTE_STEP, compute_step)
-        struct.pack_into("<I", inst.mem, me + LBM_STAT_CMAP, stat | (cmap << 8))
-        stream, cur, ids = [], None, [100]
+        stream, cur, ids = [], [None], [100]
 
         def field(v):
             if me <= v < me + 4096:
                 return [v - me, None]
-            assert arena <= v < arena + 1024 * 64, hex(v)
+            if not arena <= v < arena + 1024 * 64:
+                return [None, v]  # not a word of self: a computed number
             assert (v - arena) % 64 % 24 == 0  # a wgpu::BindGroup is 24 bytes in this build
             return [(v - arena) // 64 * 4, (v - arena) % 64 // 24]
 
         def method(k):
             def h(i, *a):
-                nonlocal cur
                 name = rev.get(k)
                 if name in ("device_create_command_encoder", "begin_compute_pass", "encoder_finish", "queue_submit"):
                     out = a[0]
@@ -299,22 +296,26 @@ class Reference:
                         stream.append(["encoder"])
                     elif name == "begin_compute_pass":
                         p, ln = i.u32(a[-1]), i.u32(a[-1] + 4)  # ComputePassDescriptor { label: Option<&str> }
-                        cur = ["pass", i.read(p, ln).decode() if p else None, None, [], None]
+                        cur[0] = ["pass", i.read(p, ln).decode() if p else None, None, [], None]
                     elif name == "queue_submit":
                         assert a[2] == drv + DRIVER_QUEUE
                         stream.append(["submit"])
                     return None
-                if name == "set_pipeline":
-                    cur[2] = field(a[4])[0]
+                if name == "queue_write_buffer":
+                    assert a[1] == drv + DRIVER_QUEUE and a[7] == 0  # offset 0
+                    stream.append(["write", a[4] - me - 48, i.read(a[8], a[9]).hex()])  # &buffer.id is 48 bytes in
+                elif name == "set_pipeline":
+                    cur[0][2] = field(a[4])[0]
                 elif name == "set_bind_group":
                     assert a[9] == 0  # no dynamic offsets
-                    cur[3].append([a[4]] + field(a[5]))
+                    cur[0][3].append([a[4]] + field(a[5]))
                 elif name == "dispatch_workgroups":
                     assert a[5] == 1 and a[6] == 1
-                    cur[4] = field(a[4])[0]  # the VALUE of a self word = its arena slot: which field was read
+                    f = field(a[4])  # the VALUE of a self word = its arena slot: which field was read
+                    cur[0][4] = f[0] if f[0] is not None else f[1]
                 elif name == "end_compute_pass":
-                    stream.append(cur)
-                    cur = None
+                    stream.append(cur[0])
+                    cur[0] = None
                 elif k in (250, 251):
                     pass
                 else:
@@ -324,12 +325,38 @@ class Reference:
 
         for k in range(nslot):
             inst.virtual_table[virt + k] = method(k)
+        return inst, me, drv, stream
+
+    def iterate_trace(self, n, compute_step=0, stat=0, cmap=2):
+        """LBM::iterate(&mut self, &driver, n) (lbm.rs:1065-1074: n x (collide; stream; compute_step += 1), then
+        calculate_summary + color_map) against the mock wgpu context; returns the command stream.  The run ends
+        when iterate reaches render() (the surface is not mocked)."""
+        inst, me, drv, stream = self._mock_wgpu()
+        struct.pack_into("<II", inst.mem, me + LBM_X, 64, 32)
+        struct.pack_into("<I", inst.mem, me + LBM_COMPUTE_STEP, compute_step)
+        struct.pack_into("<I", inst.mem, me + LBM_STAT_CMAP, stat | (cmap << 8))
         try:
             inst.call(F_ITERATE, me, drv, n)
         except Trap:
             pass  # render(): surface_get_current_texture is not mocked
         assert inst.u32(me + LBM_COMPUTE_STEP) == compute_step + n and not inst.called
         return stream
+
+    def draw_trace(self, p1, p2, xdim, ydim):
+        """LBM::draw_shape(&mut self, &driver, &Curve{line p1 -> p2}) against the mock wgpu context, to completion:
+        the two uploads, the empty submit, and the barrier_draw pass with its dispatch size (lbm.rs:1341-1356)"""
+        inst, me, drv, stream = self._mock_wgpu()
+        malloc = self.m.exports["__wbindgen_malloc"][1]
+        cur, vt = inst.call(malloc, 64, 8), inst.call(malloc, 32, 4)
+        struct.pack_into("<QQIIIIIii", inst.mem, cur, 1, 2, 0, 0, 0, self.empty_group, 1, p1[0], p1[1])
+        inst.call(F_ADD_SEGMENT, cur, p2[0] & 0xFFFFFFFF, p2[1] & 0xFFFFFFFF, xdim, ydim)
+        npoints = len(self._read_set(inst, cur))
+        struct.pack_into("<I", inst.mem, me + LBM_X, xdim)
+        struct.pack_into("<IIII", inst.mem, vt, 0, 44, 8, (1 << 20) + 200)
+        inst.virtual_table[(1 << 20) + 200] = lambda i, this: this  # Curve::get_points(&self) -> &self.points
+        inst.call(F_DRAW_SHAPE, me, drv, cur, vt)  # returns normally
+        assert not inst.called
+        return npoints, stream
 
     def line_new(self, p1, p2, xdim, ydim):
         inst, ret = self._instance()
@@ -388,7 +415,10 @@ def main():
     for stat in range(5):
         for cmap in range(3):
             out[f"iterate_trace/frame_only/{stat}/{cmap}"] = np.bytes_(json.dumps(ref.iterate_trace(0, stat=stat, cmap=cmap)))
-    print("iterate: command streams recorded", flush=True)
+    npoints, stream = ref.draw_trace((3, 4), (20, 11), 64, 32)
+    out["draw_trace/npoints"] = np.int64(npoints)
+    out["draw_trace/stream"] = np.bytes_(json.dumps(stream))
+    print("iterate, draw_shape: command streams recorded", flush=True)
     path = os.path.join(HERE, "wasm_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

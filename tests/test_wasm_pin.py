@@ -272,6 +272,42 @@ def test_dispatch_order_equals_the_reference_binarys_command_stream(golden):
     assert len(pipelines) == 15 and len({p[0] for p in pipelines}) == 5 and len({p[1] for p in pipelines}) == 3
 
 
+def test_paint_command_stream_of_the_reference_binary(golden):
+    """draw_shape run to completion against the mock wgpu context: two uploads (the pairs, then the count word), an
+    empty submit, and ONE compute pass that binds (draw group, barrier group) and dispatches exactly one workgroup
+    per painted point (barrier_draw.wgsl has @workgroup_size(1)) — what the oracle-side driver's draw_points does;
+    and the barrier group it binds is the very group the four stream passes bind at slot 3."""
+    import json
+    stream = json.loads(golden["draw_trace/stream"].item())
+    n = int(golden["draw_trace/npoints"])
+    kinds = [r[0] for r in stream]
+    assert kinds == ["write", "write", "submit", "encoder", "pass", "submit"]
+    pairs = np.frombuffer(bytes.fromhex(stream[0][2]), dtype=np.uint32)
+    count = np.frombuffer(bytes.fromhex(stream[1][2]), dtype=np.uint32)
+    assert len(pairs) == 2 * n and count.tolist() == [2 * n - 1] and stream[0][1] != stream[1][1]
+    _, label, pipeline, groups, dispatch = stream[4]
+    assert dispatch == n and [g[0] for g in groups] == [0, 1] and all(g[2] is None for g in groups)
+    step = json.loads(golden["iterate_trace/steps3_from0"].item())
+    stream_passes = [r for r in step if r[0] == "pass" and r[1] and r[1].startswith("Stream_")]
+    assert {tuple(r[3][3][1:]) for r in stream_passes} == {tuple(groups[1][1:])}  # the same barrier bind group
+    assert pipeline not in {r[2] for r in step if r[0] == "pass"}  # its own pipeline (barrier_draw.wgsl)
+    # the oracle-side driver: one dispatch of len(pairs) workgroups, group 0 = (count, updates), group 1 = barrier
+    from oracle.wgsl_interp import WgslLBM
+
+    class Recorder(WgslLBM):
+        def _load_shaders(self, root):
+            outer = self
+
+            class Draw:
+                def dispatch(self, workgroups, bindings):
+                    outer.seen = (workgroups, {g for g, _ in bindings}, bindings[(1, 0)] is outer.barrier)
+            self.sh = {"draw": Draw()}
+
+    sim = Recorder(1.0, 64, 32)
+    sim.draw_points(pairs.reshape(-1, 2))
+    assert sim.seen == (n, {0, 1}, True)
+
+
 @needs_reference
 def test_fixture_comes_from_the_binary_in_the_reference_tree_and_reruns_live(golden):
     from tests.golden.make_wasm_golden import Reference
