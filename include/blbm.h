@@ -81,6 +81,23 @@ int blbm_create(uint32_t w, uint32_t h, float omega, float inflow_ux, int device
 int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t row_end, float omega,
                      float inflow_ux, int device, blbm_t **out);
 
+/* LBM::new for lattices that need more than one GPU (lbm.rs:726; the reference is single-device): the lattice is
+ * cut into ndev y-slabs (contiguous row ranges whose sizes differ by at most one row, top slab on devices[0]), one
+ * per listed device (a device may be listed more than once), linked to their neighbours, and returned as ONE handle.
+ * Every entry point of this header accepts it: mutators are applied to all slabs in lock-step (one host thread
+ * enqueues the slabs' work in interleaved chunks), read-backs return the whole lattice, rows x W, top to bottom;
+ * blbm_timer_stop / blbm_iterate_timed report the slowest slab.  ndev == 1 is blbm_create on devices[0].  Peer access
+ * between the listed devices must be possible (NVLink / NVSwitch on a B200 node).  Group handles cannot be linked
+ * further (blbm_export_peer / blbm_link_* fail with BLBM_ESTATE). */
+int blbm_create_group(uint32_t w, uint64_t h, float omega, float inflow_ux, const int *devices, int ndev,
+                      blbm_t **out);
+/* number of slabs behind a handle (1 for plain handles) and access to one of them, e.g. for per-slab tuning or
+ * geometry; the slab stays owned by the group */
+int blbm_group_size(const blbm_t *h);
+int blbm_group_slab(blbm_t *h, int index, blbm_t **slab);
+
+/* Linked slabs (and group handles) must not be destroyed while a neighbour still has steps in flight that store into
+ * them: destroy waits (bounded) for both neighbours to reach this slab's epoch before it frees the pool. */
 int blbm_destroy(blbm_t *h);
 
 /* ---- the per-timestep update ----------------------------------------------------------------- */

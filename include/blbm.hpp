@@ -33,8 +33,13 @@ enum class SummaryStat { Curl = 0, Ux = 1, Uy = 2, Rho = 3, Speed = 4 };
 enum class ColorMap { Inferno = 0, Viridis = 1, Jet = 2 };
 
 // driver.rs:1-7: the wgpu device/queue/surface bundle; the CUDA device and stream live inside the handle
+// One device: the whole lattice on it.  Several: the lattice is cut into y-slabs, one per listed device, behind
+// the same LBM value (blbm_create_group).
 struct Driver {
-    int device = 0;
+    std::vector<int> devices{0};
+    Driver() {}
+    explicit Driver(int device) : devices{device} {}
+    explicit Driver(const std::vector<int> &devs) : devices(devs) {}
 };
 
 // barrier_shapes/mod.rs:11-19
@@ -130,7 +135,7 @@ public:
     // LBM::new(&driver, omega, x, y), lbm.rs:726
     LBM(const Driver &driver, float omega, std::uint32_t x, std::uint32_t y) : x_(x), y_(y)
     {
-        check(blbm_create(x, y, omega, 0.1f, driver.device, &h_));
+        check(blbm_create_group(x, y, omega, 0.1f, driver.devices.data(), (int)driver.devices.size(), &h_));
     }
     ~LBM() { blbm_destroy(h_); }
     LBM(const LBM &) = delete;

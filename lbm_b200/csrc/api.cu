@@ -16,31 +16,19 @@
 #include <unistd.h>
 #include <vector>
 
-#include "../../include/blbm.h"
-#include "blbm_internal.cuh"
+#include "handle.cuh"
+#include "group.h"
 
 using namespace blbmk;
 
 namespace {
 
+using blbmh::fail;
+using blbmh::Peer;
+using blbmh::PeerBlob;
+using blbmh::PEER_MAGIC;
+
 thread_local char g_err[512] = "";
-
-int fail(int code, const char *fmt, ...)
-{
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define CK(call)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e__ = (call);                                                                         \
-        if (e__ != cudaSuccess)                                                                           \
-            return fail(BLBM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,    \
-                        __LINE__);                                                                        \
-    } while (0)
 
 #define CKH(h)                                                                  \
     do {                                                                        \
@@ -48,101 +36,16 @@ int fail(int code, const char *fmt, ...)
         CK(cudaSetDevice((h)->device));                                         \
     } while (0)
 
-constexpr uint32_t PEER_MAGIC = 0xB1B30001u;
-
-// what a neighbour needs to know to store into our halo rows
-struct PeerBlob {
-    uint32_t magic;
-    uint32_t W, P, rows;
-    uint64_t row0, row1, Hg;
-    uint64_t pool_bytes;
-    uint64_t off_f[2][8];
-    uint64_t off_mx, off_my;
-    uint64_t off_flags;
-    int32_t device;
-    int32_t pid;
-    uint64_t local_ptr;  // pool base in the exporting process (used when pid matches)
-    cudaIpcMemHandle_t ipc;
-};
-static_assert(sizeof(PeerBlob) <= BLBM_PEER_HANDLE_BYTES, "peer blob too large");
-
-struct Peer {
-    bool linked = false;
-    bool ipc_opened = false;
-    char *base = nullptr;  // neighbour's pool mapped into this process / device
-    PeerBlob info{};
-};
-
 }  // namespace
 
-struct blbm_handle {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // asynchronous read-back of the output field: a second stream so the copy overlaps later steps
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_sum = nullptr, ev_copy = nullptr;
-    bool copy_pending = false;
-    uint32_t W = 0, P = 0, rows = 0;
-    uint64_t Hg = 0, row0 = 0, row1 = 0;
-    size_t plane = 0;  // elements per population plane, (rows+3)*P
-    char *pool = nullptr;
-    size_t pool_bytes = 0;
-    float *f[2][8] = {};
-    float *R = nullptr, *mx = nullptr, *my = nullptr, *rho = nullptr, *out = nullptr;
-    uint16_t *cls[2] = {};
-    uint8_t *rowflag[2] = {};  // per class buffer: one byte per (row, 128-cell chunk), see build_class_kernel
-    uint8_t *mask = nullptr;
-    unsigned long long *flags = nullptr;  // [0] epoch from the slab above, [16] from below (128 B apart)
-    int *err_flag = nullptr;
-    double *red_sums = nullptr;
-    float *red_max = nullptr;
-    size_t off_f[2][8] = {};
-    size_t off_mx = 0, off_my = 0, off_flags = 0;
-    int cls_cur = 0;
-    bool cls_pending = false;  // the mask changed while a stream was pending: cls[cls_cur^1] is newer
-    // owned rows in which the two class buffers may differ (a paint rebuilds only the rows it touches)
-    uint32_t diff_lo = 0, diff_hi = 0;
-    bool regimeT = false;
-    bool halo_dirty = false;
-    float omega = 1.0f;
-    int stat = BLBM_CURL;
-    uint64_t step = 0, frame = 0;
-    int kernel = BLBM_KERNEL_VEC4;
-    int vec4_dense = -1;  // bounce-back flavour of the vec4 kernel: -1 auto, 0 sparse, 1 dense
-    int vec4_packed = 0;  // 1: collide cell pairs with packed fp32 adds (FADD2): same bits, but measured slower (registers)
-    int vec4_index32 = -1;  // 32-bit plane offsets in the vec4 kernel (plane < 2^32 elements): -1 auto, 0, 1
-    int vec4_rows = 4;  // rows per block of the vec4 kernel (tuning knob; 4 measured best on the porous case)
-    // TMA-staged kernel: tensor maps (opaque 128-byte descriptors) and launch shape
-    alignas(64) unsigned char tma_maps[16 * 128];
-    alignas(64) unsigned char tma_map_rest[128];
-    bool tma_ready = false;
-    int tma_rows = 4, tma_stages = 4, tma_ctas = 2;
-    uint64_t launches = 0;
-    Peer up, dn;
-    unsigned long long epoch = 0, waited = 0;
-    unsigned long long wait_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
-    uint64_t *d_pairs = nullptr;
-    size_t d_pairs_cap = 0;
-    // barrier chains (lazy barrier cells): see aux_kernels.cu
-    int lazy_mode = 2;           // 0 never, 1 always, 2 auto (enough barrier cells and enough steps to pay off)
-    bool chain_active = false;   // barrier slots of the planes are don't-care, their state is in the table
-    bool chain_declined = false; // auto mode looked at the current mask and decided against
-    uint32_t *chain_idx = nullptr;
-    float *chain_state = nullptr;
-    size_t chain_n = 0, chain_cap = 0;
-    unsigned long long *chain_counter = nullptr;
-    unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
-    // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): GRAPH_CHUNK fused steps are
-    // captured once into a CUDA graph per start parity and replayed.
-    struct StepGraph {
-        cudaGraphExec_t exec = nullptr;
-        unsigned long long sig[4] = {0, 0, 0, 0};
-    } graph[2];
-    int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
-    float *rgb = nullptr;  // colour buffer (rows x W x 3), allocated by the first blbm_color_map
-};
-typedef blbm_handle blbm;
+int blbmh::fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 
 namespace {
 
@@ -437,13 +340,13 @@ int run_step_graph(blbm *h)
     return BLBM_OK;
 }
 
-int do_steps(blbm *h, uint32_t n)
+int do_steps(blbm *h, uint32_t n, bool store_moments = true)
 {
     uint32_t left = n;
     bool replayed = false;
     const bool graphs = graphs_wanted(h);
     while (left) {
-        const bool mom = left == 1;
+        const bool mom = left == 1 && store_moments;
         int rc;
         if (!h->chain_active && (rc = chain_try_enter(h, left)) != BLBM_OK) return rc;
         if (h->chain_active && !replayed) {
@@ -590,19 +493,21 @@ int fill_equilibrium(blbm *h, float ux, int single_index)
             const int64_t gy = flat / x, gx = flat % x;
             const int64_t dr = gy - (int64_t)h->row0 + 1;  // device row
             if (dr >= (int64_t)r_begin && dr < (int64_t)r_end) {
-                const float four = 4.0f;
+                // one-cell fills through the fill kernel: no host buffer, no host synchronisation
                 const size_t off = (size_t)dr * h->P + (size_t)gx;
+                float *cell[2];
+                const float four[2] = {4.0f, 4.0f};
+                int nc = 0;
                 if (single_index == BLBM_REST) {
-                    CK(cudaMemcpyAsync(h->R + off, &four, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+                    cell[nc++] = h->R + off;
                 } else {
                     int d = 0;
                     for (int q = 0; q < 8; q++)
                         if (pop_of_dir[q] == single_index) d = q;
-                    for (int b = 0; b < 2; b++)
-                        CK(cudaMemcpyAsync(h->f[b][d] + off, &four, sizeof(float), cudaMemcpyHostToDevice,
-                                           h->stream));
+                    for (int b = 0; b < 2; b++) cell[nc++] = h->f[b][d] + off;
                 }
-                CK(cudaStreamSynchronize(h->stream));  // `four` lives on this stack frame
+                CK(launch_fill_rows(cell, four, nc, 1, 1, 0, 1, h->stream));
+                h->launches++;
             }
         }
     }
@@ -728,6 +633,26 @@ int attach_peer(blbm *h, int side, const PeerBlob &b, char *base, bool ipc_opene
 // ================================================================================================
 // C ABI
 // ================================================================================================
+int blbmh::slab_steps(blbm *h, uint32_t n, bool store_moments)
+{
+    CKH(h);
+    return do_steps(h, n, store_moments);
+}
+
+int blbmh::slab_summary(blbm *h)
+{
+    CKH(h);
+    return run_summary(h);
+}
+
+// group handles (blbm_create_group): hand the call to the fan-out of the same name in group.cu
+#define GRP(h, expr)                                \
+    do {                                            \
+        if ((h) && (h)->group) return (expr);       \
+    } while (0)
+#define GRP_EACH(h, call) GRP(h, blbmh::group_each(h, [&](blbm *s) { return call; }))
+using namespace blbmh;
+
 extern "C" {
 
 const char *blbm_last_error(void) { return g_err; }
@@ -827,10 +752,16 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
             (ce = cudaEventCreate(&h->ev0)) != cudaSuccess || (ce = cudaEventCreate(&h->ev1)) != cudaSuccess ||
             (ce = cudaEventCreateWithFlags(&h->ev_sum, cudaEventDisableTiming)) != cudaSuccess ||
             (ce = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
+            (ce = cudaHostAlloc((void **)&h->stage_host, blbm::STAGE_SLOTS * blbm::STAGE_PAIRS * 2 * sizeof(uint64_t),
+                                cudaHostAllocDefault)) != cudaSuccess ||
             (ce = cudaMemsetAsync(h->pool, 0, h->pool_bytes, h->stream)) != cudaSuccess) {
             rc = fail(BLBM_ECUDA, "handle setup failed: %s", cudaGetErrorString(ce));
             break;
         }
+        for (int q = 0; q < blbm::STAGE_SLOTS && rc == BLBM_OK; q++)
+            if ((ce = cudaEventCreateWithFlags(&h->stage_ev[q], cudaEventDisableTiming)) != cudaSuccess)
+                rc = fail(BLBM_ECUDA, "handle setup failed: %s", cudaGetErrorString(ce));
+        if (rc != BLBM_OK) break;
         if ((rc = fill_equilibrium(h, inflow_ux, -1)) != BLBM_OK) break;
         if ((ce = launch_mask_init(h->mask, geom(h), h->stream)) != cudaSuccess ||
             (ce = launch_build_class(h->cls[0], h->mask, geom(h), nullptr, h->rowflag[0], 0, h->rows, h->stream)) !=
@@ -861,8 +792,19 @@ int blbm_create(uint32_t w, uint32_t hgt, float omega, float inflow_ux, int devi
 
 int blbm_destroy(blbm_t *h)
 {
+    GRP(h, group_destroy(h));
     if (!h) return BLBM_OK;
     cudaSetDevice(h->device);
+    if (h->stream && any_peer(h)) {
+        // Neighbours store into this pool from their step kernels.  All linked slabs run the same call sequence, so
+        // once both neighbours have published our current epoch they have nothing left in flight that targets us;
+        // wait for that (bounded: a neighbour that died early must not stall the destructor for long).
+        const unsigned long long keep = h->wait_timeout_ns;
+        h->wait_timeout_ns = std::min<unsigned long long>(keep, 2ull * 1000ull * 1000ull * 1000ull);
+        h->waited = 0;
+        sync_peers(h);
+        h->wait_timeout_ns = keep;
+    }
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->up.ipc_opened) cudaIpcCloseMemHandle(h->up.base);
     if (h->dn.ipc_opened) cudaIpcCloseMemHandle(h->dn.base);
@@ -876,6 +818,9 @@ int blbm_destroy(blbm_t *h)
     for (int q = 0; q < 2; q++)
         if (h->graph[q].exec) cudaGraphExecDestroy(h->graph[q].exec);
     if (h->mailbox_host) cudaFreeHost(h->mailbox_host);
+    if (h->stage_host) cudaFreeHost(h->stage_host);
+    for (int q = 0; q < blbm::STAGE_SLOTS; q++)
+        if (h->stage_ev[q]) cudaEventDestroy(h->stage_ev[q]);
     if (h->pool) cudaFree(h->pool);
     if (h->copy_stream) {
         cudaStreamSynchronize(h->copy_stream);
@@ -892,6 +837,7 @@ int blbm_destroy(blbm_t *h)
 
 int blbm_iterate(blbm_t *h, uint32_t n)
 {
+    GRP(h, group_steps(h, n, true, true));
     CKH(h);
     int rc = do_steps(h, n);
     if (rc) return rc;
@@ -903,12 +849,14 @@ int blbm_iterate(blbm_t *h, uint32_t n)
 
 int blbm_advance(blbm_t *h, uint32_t n)
 {
+    GRP(h, group_steps(h, n, false, false));
     CKH(h);
     return do_steps(h, n);
 }
 
 int blbm_iterate_timed(blbm_t *h, uint32_t n, float *elapsed_ms)
 {
+    GRP(h, group_iterate_timed(h, n, elapsed_ms));
     CKH(h);
     if (!elapsed_ms) return fail(BLBM_EINVAL, "elapsed_ms is null");
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -925,6 +873,7 @@ int blbm_iterate_timed(blbm_t *h, uint32_t n, float *elapsed_ms)
 
 int blbm_timer_start(blbm_t *h)
 {
+    GRP(h, group_timer_start(h));
     CKH(h);
     CK(cudaEventRecord(h->ev0, h->stream));
     return BLBM_OK;
@@ -932,6 +881,7 @@ int blbm_timer_start(blbm_t *h)
 
 int blbm_timer_stop(blbm_t *h, float *elapsed_ms)
 {
+    GRP(h, group_timer_stop(h, elapsed_ms));
     CKH(h);
     if (!elapsed_ms) return fail(BLBM_EINVAL, "elapsed_ms is null");
     if (h->copy_pending) CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));  // the stopwatch covers the copy
@@ -943,6 +893,7 @@ int blbm_timer_stop(blbm_t *h, float *elapsed_ms)
 
 int blbm_collide(blbm_t *h)
 {
+    GRP_EACH(h, blbm_collide(s));
     CKH(h);
     int rc = chain_flush(h);
     if (rc) return rc;
@@ -954,6 +905,7 @@ int blbm_collide(blbm_t *h)
 
 int blbm_stream(blbm_t *h)
 {
+    GRP_EACH(h, blbm_stream(s));
     CKH(h);
     int rc = chain_flush(h);
     if (rc) return rc;
@@ -965,6 +917,7 @@ int blbm_stream(blbm_t *h)
 
 int blbm_set_summary(blbm_t *h, int stat)
 {
+    GRP_EACH(h, blbm_set_summary(s, stat));
     if (!h) return fail(BLBM_EINVAL, "null handle");
     if (stat < 0 || stat > 4) return fail(BLBM_EINVAL, "stat %d out of range", stat);
     h->stat = stat;
@@ -973,6 +926,7 @@ int blbm_set_summary(blbm_t *h, int stat)
 
 int blbm_rerender(blbm_t *h)
 {
+    GRP(h, group_steps(h, 0, true, true));
     CKH(h);
     int rc = run_summary(h);
     if (rc) return rc;
@@ -982,6 +936,7 @@ int blbm_rerender(blbm_t *h)
 
 int blbm_compute_summary(blbm_t *h, int stat)
 {
+    GRP_EACH(h, blbm_compute_summary(s, stat));
     CKH(h);
     int rc = blbm_set_summary(h, stat);
     if (rc) return rc;
@@ -990,6 +945,7 @@ int blbm_compute_summary(blbm_t *h, int stat)
 
 int blbm_set_omega(blbm_t *h, float omega)
 {
+    GRP_EACH(h, blbm_set_omega(s, omega));
     if (!h) return fail(BLBM_EINVAL, "null handle");
     h->omega = omega;
     return BLBM_OK;
@@ -997,26 +953,35 @@ int blbm_set_omega(blbm_t *h, float omega)
 
 int blbm_custom_speed(blbm_t *h, float ux)
 {
+    GRP_EACH(h, blbm_custom_speed(s, ux));
     CKH(h);
+    // collective over linked slabs: wait until the neighbours' last pushes into our halo rows have landed, refill,
+    // then publish a new epoch so that no neighbour's next launch stores into our halo rows before our fill ran
     int rc = sync_peers(h);
     if (rc) return rc;
     rc = fill_equilibrium(h, ux, -1);
     if (rc) return rc;
-    return moments_without_rest(h);
+    rc = moments_without_rest(h);
+    if (rc) return rc;
+    return signal_peers(h);
 }
 
 int blbm_reset_to_equilibrium(blbm_t *h) { return blbm_custom_speed(h, 0.1f); }
 
 int blbm_single_cell(blbm_t *h, uint32_t index)
 {
+    GRP_EACH(h, blbm_single_cell(s, index));
     CKH(h);
     int rc = sync_peers(h);
     if (rc) return rc;
-    return fill_equilibrium(h, 0.0f, index <= 8 ? (int)index : 9);
+    rc = fill_equilibrium(h, 0.0f, index <= 8 ? (int)index : 9);
+    if (rc) return rc;
+    return signal_peers(h);  // see blbm_custom_speed
 }
 
 int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
 {
+    GRP_EACH(h, blbm_draw_points64(s, pairs, npairs));
     CKH(h);
     if (npairs == 0) return BLBM_OK;
     if (!pairs) return fail(BLBM_EINVAL, "pairs is null");
@@ -1063,7 +1028,20 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
             if (e != cudaSuccess) return fail(BLBM_ENOMEM, "allocating the paint list failed");
             h->d_pairs_cap = cap;
         }
-        CK(cudaMemcpyAsync(h->d_pairs, uniq.data(), nu * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        const bool staged = nu <= blbm::STAGE_PAIRS;
+        if (staged) {
+            // through the pinned ring: the upload is asynchronous and the caller's buffer is free on return
+            const int slot = h->stage_next;
+            h->stage_next = (slot + 1) % blbm::STAGE_SLOTS;
+            if (h->stage_used[slot]) CK(cudaEventSynchronize(h->stage_ev[slot]));  // long done unless 4 paints are queued
+            uint64_t *st = h->stage_host + (size_t)slot * blbm::STAGE_PAIRS * 2;
+            memcpy(st, uniq.data(), nu * 2 * sizeof(uint64_t));
+            CK(cudaMemcpyAsync(h->d_pairs, st, nu * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaEventRecord(h->stage_ev[slot], h->stream));
+            h->stage_used[slot] = true;
+        } else {
+            CK(cudaMemcpyAsync(h->d_pairs, uniq.data(), nu * 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        }
         if (h->chain_active) {
             // cells about to change leave the chain table first (their state returns to the planes)
             CK(launch_chain_evict(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, chain_planes(h),
@@ -1072,7 +1050,7 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         }
         CK(launch_mask_scatter(h->mask, geom(h), h->d_pairs, nu, h->stream));
         h->launches++;
-        CK(cudaStreamSynchronize(h->stream));  // uniq is pageable host memory owned by this frame
+        if (!staged) CK(cudaStreamSynchronize(h->stream));  // uniq is pageable host memory owned by this frame
     }
     return rebuild_class(h, rlo, rhi, nu * 100ull >= (unsigned long long)h->rows * h->W);
 }
@@ -1094,6 +1072,7 @@ int blbm_draw_points(blbm_t *h, const uint32_t *pairs, size_t npairs)
 
 int blbm_reset_barrier(blbm_t *h)
 {
+    GRP_EACH(h, blbm_reset_barrier(s));
     CKH(h);
     {
         int rcf = chain_flush(h);
@@ -1106,6 +1085,7 @@ int blbm_reset_barrier(blbm_t *h)
 
 int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const uint8_t *mask)
 {
+    GRP_EACH(h, blbm_write_barrier_rows(s, row_begin, nrows, mask));
     CKH(h);
     if (!mask && nrows) return fail(BLBM_EINVAL, "mask is null");
     {
@@ -1126,8 +1106,8 @@ int blbm_write_barrier_rows(blbm_t *h, uint64_t row_begin, uint64_t nrows, const
     return rebuild_class(h, 0, h->rows, true);
 }
 
-uint64_t blbm_get_compute_num(const blbm_t *h) { return h ? h->step : 0; }
-uint64_t blbm_get_frame_num(const blbm_t *h) { return h ? h->frame : 0; }
+uint64_t blbm_get_compute_num(const blbm_t *h) { return !h ? 0 : h->group ? h->group->slabs.front()->step : h->step; }
+uint64_t blbm_get_frame_num(const blbm_t *h) { return !h ? 0 : h->group ? h->group->slabs.front()->frame : h->frame; }
 
 static int copy_plane_to_host(blbm *h, const float *plane, float *dst)
 {
@@ -1146,6 +1126,7 @@ static float *population_plane(blbm *h, int buffer, int k)
 
 int blbm_read_population(blbm_t *h, int buffer, int k, float *dst)
 {
+    GRP(h, group_read_rows(h, GR_POPULATION, buffer, k, dst, nullptr, nullptr));
     CKH(h);
     if (!dst || k < 0 || k > 8 || buffer < -1 || buffer > 1) return fail(BLBM_EINVAL, "bad argument");
     int rc = chain_flush(h);
@@ -1159,6 +1140,7 @@ int blbm_read_population(blbm_t *h, int buffer, int k, float *dst)
 
 int blbm_write_population(blbm_t *h, int buffer, int k, const float *src)
 {
+    GRP(h, group_write_population(h, buffer, k, src));
     CKH(h);
     if (!src || k < 0 || k > 8 || buffer < -1 || buffer > 1) return fail(BLBM_EINVAL, "bad argument");
     int rc = chain_flush(h);
@@ -1174,6 +1156,7 @@ int blbm_write_population(blbm_t *h, int buffer, int k, const float *src)
 
 int blbm_read_moments(blbm_t *h, float *mx, float *my, float *rho)
 {
+    GRP(h, group_read_rows(h, GR_MOMENTS, 0, 0, mx, my, rho));
     CKH(h);
     int rc;
     if (mx && (rc = copy_plane_to_host(h, h->mx, mx))) return rc;
@@ -1184,6 +1167,7 @@ int blbm_read_moments(blbm_t *h, float *mx, float *my, float *rho)
 
 int blbm_read_output(blbm_t *h, float *dst)
 {
+    GRP(h, group_read_rows(h, GR_OUTPUT, 0, 0, dst, nullptr, nullptr));
     CKH(h);
     if (!dst) return fail(BLBM_EINVAL, "dst is null");
     int rc = copy_plane_to_host(h, h->out, dst);
@@ -1193,6 +1177,7 @@ int blbm_read_output(blbm_t *h, float *dst)
 
 int blbm_color_map(blbm_t *h, int map)
 {
+    GRP_EACH(h, blbm_color_map(s, map));
     CKH(h);
     if (map < 0 || map > 2) return fail(BLBM_EINVAL, "colour map %d out of range", map);
     if (!h->rgb) {
@@ -1210,6 +1195,7 @@ int blbm_color_map(blbm_t *h, int map)
 
 int blbm_read_colors(blbm_t *h, float *rgb)
 {
+    GRP(h, group_read_rows(h, GR_COLORS, 0, 0, rgb, nullptr, nullptr));
     CKH(h);
     if (!rgb) return fail(BLBM_EINVAL, "rgb is null");
     if (!h->rgb) return fail(BLBM_ESTATE, "blbm_color_map has not been called");
@@ -1219,6 +1205,7 @@ int blbm_read_colors(blbm_t *h, float *rgb)
 
 int blbm_read_output_async(blbm_t *h, float *pinned_dst)
 {
+    GRP(h, group_read_rows(h, GR_OUTPUT_ASYNC, 0, 0, pinned_dst, nullptr, nullptr));
     CKH(h);
     if (!pinned_dst) return fail(BLBM_EINVAL, "dst is null");
     // order the copy after everything enqueued so far, but run it on the copy stream so that the steps
@@ -1236,12 +1223,14 @@ int blbm_read_output_async(blbm_t *h, float *pinned_dst)
 
 int blbm_synchronize(blbm_t *h)
 {
+    GRP_EACH(h, blbm_synchronize(s));
     CKH(h);
     return sync_stream(h);
 }
 
 int blbm_read_barrier(blbm_t *h, uint32_t *dst)
 {
+    GRP(h, group_read_rows(h, GR_BARRIER, 0, 0, dst, nullptr, nullptr));
     CKH(h);
     if (!dst) return fail(BLBM_EINVAL, "dst is null");
     std::vector<uint8_t> tmp;
@@ -1260,6 +1249,7 @@ int blbm_read_barrier(blbm_t *h, uint32_t *dst)
 
 int blbm_read_cell_class(blbm_t *h, uint16_t *dst)
 {
+    GRP(h, group_read_rows(h, GR_CLASS, 0, 0, dst, nullptr, nullptr));
     CKH(h);
     if (!dst) return fail(BLBM_EINVAL, "dst is null");
     // the kernel-facing class words use an internal encoding; the public word is derived from the (current)
@@ -1280,6 +1270,7 @@ int blbm_read_cell_class(blbm_t *h, uint16_t *dst)
 
 int blbm_reduce_moments(blbm_t *h, double *sum_rho, double *sum_mx, double *sum_my, float *max_abs_output)
 {
+    GRP(h, group_reduce_moments(h, sum_rho, sum_mx, sum_my, max_abs_output));
     CKH(h);
     CK(launch_reduce(h->mx, h->my, h->rho, h->out, geom(h), h->red_sums, h->red_max, h->stream));
     h->launches++;
@@ -1299,6 +1290,7 @@ int blbm_reduce_moments(blbm_t *h, double *sum_rho, double *sum_mx, double *sum_
 int blbm_get_geometry(const blbm_t *h, uint32_t *w, uint64_t *h_global, uint64_t *row_begin, uint64_t *row_end,
                       int *device)
 {
+    GRP(h, group_get_geometry(h, w, h_global, row_begin, row_end, device));
     if (!h) return fail(BLBM_EINVAL, "null handle");
     if (w) *w = h->W;
     if (h_global) *h_global = h->Hg;
@@ -1310,6 +1302,7 @@ int blbm_get_geometry(const blbm_t *h, uint32_t *w, uint64_t *h_global, uint64_t
 
 int blbm_export_peer(blbm_t *h, void *blob)
 {
+    GRP(h, fail(BLBM_ESTATE, "a group handle links its slabs itself"));
     CKH(h);
     if (!blob) return fail(BLBM_EINVAL, "blob is null");
     PeerBlob b;
@@ -1322,6 +1315,7 @@ int blbm_export_peer(blbm_t *h, void *blob)
 
 int blbm_link_peer(blbm_t *h, int side, const void *blob)
 {
+    GRP(h, fail(BLBM_ESTATE, "a group handle links its slabs itself"));
     CKH(h);
     if (!blob || (side != 0 && side != 1)) return fail(BLBM_EINVAL, "bad argument");
     PeerBlob b;
@@ -1353,6 +1347,7 @@ int blbm_link_peer(blbm_t *h, int side, const void *blob)
 
 int blbm_link_local(blbm_t *upper, blbm_t *lower)
 {
+    if ((upper && upper->group) || (lower && lower->group)) return fail(BLBM_ESTATE, "a group handle links its slabs itself");
     if (!upper || !lower) return fail(BLBM_EINVAL, "null handle");
     unsigned char bu[BLBM_PEER_HANDLE_BYTES], bl[BLBM_PEER_HANDLE_BYTES];
     PeerBlob b;
@@ -1369,6 +1364,7 @@ int blbm_link_local(blbm_t *upper, blbm_t *lower)
 
 int blbm_exchange_halos(blbm_t *h)
 {
+    GRP_EACH(h, blbm_exchange_halos(s));
     CKH(h);
     if (!any_peer(h)) return BLBM_OK;
     int rc = chain_flush(h);
@@ -1389,6 +1385,7 @@ static int tma_prepare(blbm *h)
 
 int blbm_set_kernel(blbm_t *h, int kernel)
 {
+    GRP_EACH(h, blbm_set_kernel(s, kernel));
     CKH(h);
     switch (kernel) {
     case BLBM_KERNEL_AUTO: h->kernel = BLBM_KERNEL_VEC4; break;
@@ -1407,10 +1404,11 @@ int blbm_set_kernel(blbm_t *h, int kernel)
     return BLBM_OK;
 }
 
-int blbm_get_kernel(const blbm_t *h) { return h ? h->kernel : BLBM_EINVAL; }
+int blbm_get_kernel(const blbm_t *h) { return !h ? BLBM_EINVAL : h->group ? h->group->slabs.front()->kernel : h->kernel; }
 
 int blbm_set_tuning(blbm_t *h, int knob, int value)
 {
+    GRP_EACH(h, blbm_set_tuning(s, knob, value));
     if (!h) return fail(BLBM_EINVAL, "null handle");
     switch (knob) {
     case BLBM_TUNE_VEC4_BLOCK_ROWS:
@@ -1456,6 +1454,7 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
 
 int blbm_set_lazy_barriers(blbm_t *h, int mode)
 {
+    GRP_EACH(h, blbm_set_lazy_barriers(s, mode));
     CKH(h);
     if (mode < 0 || mode > 2) return fail(BLBM_EINVAL, "mode %d out of range", mode);
     if (mode == 0) {
@@ -1467,8 +1466,16 @@ int blbm_set_lazy_barriers(blbm_t *h, int mode)
     return BLBM_OK;
 }
 
-int blbm_get_lazy_barriers_active(const blbm_t *h) { return h && h->chain_active ? 1 : 0; }
-uint64_t blbm_get_launch_count(const blbm_t *h) { return h ? h->launches : 0; }
-uint64_t blbm_get_device_bytes(const blbm_t *h) { return h ? h->pool_bytes : 0; }
+int blbm_get_lazy_barriers_active(const blbm_t *h)
+{
+    if (h && h->group) {
+        for (const blbm *s : h->group->slabs)
+            if (s->chain_active) return 1;
+        return 0;
+    }
+    return h && h->chain_active ? 1 : 0;
+}
+uint64_t blbm_get_launch_count(const blbm_t *h) { return !h ? 0 : h->group ? group_sum(h, GS_LAUNCHES) : h->launches; }
+uint64_t blbm_get_device_bytes(const blbm_t *h) { return !h ? 0 : h->group ? group_sum(h, GS_BYTES) : h->pool_bytes; }
 
 }  // extern "C"

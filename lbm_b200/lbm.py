@@ -79,6 +79,9 @@ PROTOTYPES = {
     "blbm_device_count": (_I, []),
     "blbm_create": (_I, [_U32, _U32, _F, _F, _I, C.POINTER(_P)]),
     "blbm_create_slab": (_I, [_U32, _U64, _U64, _U64, _F, _F, _I, C.POINTER(_P)]),
+    "blbm_create_group": (_I, [_U32, _U64, _F, _F, C.POINTER(_I), _I, C.POINTER(_P)]),
+    "blbm_group_size": (_I, [_P]),
+    "blbm_group_slab": (_I, [_P, _I, C.POINTER(_P)]),
     "blbm_destroy": (_I, [_P]),
     "blbm_iterate": (_I, [_P, _U32]),
     "blbm_advance": (_I, [_P, _U32]),
@@ -158,18 +161,29 @@ def _check(rc):
 
 
 class LBM:
-    """One slab of a D2Q9 BGK lattice on one B200 (the whole lattice unless `rows` is given)."""
+    """A D2Q9 BGK lattice: the whole lattice on one B200, one y-slab of it (`rows`), or — `devices=[...]` — the
+    whole lattice cut into y-slabs over several B200s behind one handle (blbm_create_group)."""
 
-    def __init__(self, omega, x, y, inflow_ux=0.1, device=0, rows=None, kernel=Kernel.Auto, lazy_barriers=None):
+    def __init__(self, omega, x, y, inflow_ux=0.1, device=0, rows=None, kernel=Kernel.Auto, lazy_barriers=None,
+                 devices=None):
         self._L = load_library()
         self._h = _P()
         self.x, self.y = int(x), int(y)
-        if rows is None:
-            rows = (0, self.y)
-        self.row_begin, self.row_end = int(rows[0]), int(rows[1])
-        self.device = int(device)
-        _check(self._L.blbm_create_slab(self.x, self.y, self.row_begin, self.row_end, float(omega),
-                                        float(inflow_ux), self.device, C.byref(self._h)))
+        if devices is not None:
+            if rows is not None:
+                raise ValueError("rows= and devices= are mutually exclusive")
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.row_begin, self.row_end = 0, self.y
+            self.device = int(devices[0]) if len(devices) else 0
+            _check(self._L.blbm_create_group(self.x, self.y, float(omega), float(inflow_ux), devs, len(devices),
+                                             C.byref(self._h)))
+        else:
+            if rows is None:
+                rows = (0, self.y)
+            self.row_begin, self.row_end = int(rows[0]), int(rows[1])
+            self.device = int(device)
+            _check(self._L.blbm_create_slab(self.x, self.y, self.row_begin, self.row_end, float(omega),
+                                            float(inflow_ux), self.device, C.byref(self._h)))
         self.summary_stat = SummaryStat.Curl
         if kernel != Kernel.Auto:
             self.set_kernel(kernel)
@@ -423,95 +437,15 @@ def slab_rows(y, nslabs):
     return out
 
 
-class SlabGroup:
-    """A lattice split into y-slabs over several GPUs of THIS process, presented with the same methods
-    as `LBM`.  (One-process-per-GPU deployments link `LBM(rows=...)` slabs with export_peer/link_peer
-    instead; see bench.py.)"""
+class SlabGroup(LBM):
+    """A lattice split into y-slabs over several GPUs of THIS process: `LBM(devices=[...])`, i.e. one
+    blbm_create_group handle — the slab orchestration lives behind the C ABI.  (One-process-per-GPU deployments
+    link `LBM(rows=...)` slabs with export_peer/link_peer instead; see bench.py.)"""
 
     def __init__(self, omega, x, y, devices, inflow_ux=0.1, kernel=Kernel.Auto, lazy_barriers=None):
-        self.x, self.y = int(x), int(y)
+        super().__init__(omega, x, y, inflow_ux=inflow_ux, kernel=kernel, lazy_barriers=lazy_barriers,
+                         devices=list(devices))
         self.ranges = slab_rows(y, len(devices))
-        self.slabs = [LBM(omega, x, y, inflow_ux, dev, rows=r, kernel=kernel, lazy_barriers=lazy_barriers)
-                      for dev, r in zip(devices, self.ranges)]
-        L = load_library()
-        for up, lo in zip(self.slabs[:-1], self.slabs[1:]):
-            _check(L.blbm_link_local(up._h, lo._h))
 
-    def close(self):
-        for s in self.slabs:
-            s.close()
-
-    def _all(self, name, *a):
-        return [getattr(s, name)(*a) for s in self.slabs]
-
-    def advance(self, n, chunk=32):
-        left = int(n)
-        while left > 0:
-            c = min(chunk, left)
-            self._all("advance", c)
-            left -= c
-
-    def iterate(self, n, chunk=32):
-        # interleave the slabs' launch queues: a slab's stream waits on its neighbours every step, so
-        # never enqueue one slab far ahead of the others from a single host thread
-        left = int(n)
-        while left > 0:
-            c = min(chunk, left)
-            self._all("advance", c)
-            left -= c
-        self._all("rerender")
-
-    def collide(self):
-        self._all("collide")
-
-    def stream(self):
-        self._all("stream")
-
-    def rerender(self):
-        self._all("rerender")
-
-    def set_summary(self, stat):
-        self._all("set_summary", stat)
-
-    def compute_summary(self, stat):
-        self._all("compute_summary", stat)
-
-    def update_omega_buffer(self, omega):
-        self._all("update_omega_buffer", omega)
-
-    def reset_to_equilibrium(self):
-        self._all("reset_to_equilibrium")
-
-    def custom_speed(self, ux):
-        self._all("custom_speed", ux)
-
-    def single_cell(self, index):
-        self._all("single_cell", index)
-
-    def draw_points(self, pairs):
-        self._all("draw_points", pairs)
-
-    def reset_barrier(self):
-        self._all("reset_barrier")
-
-    def synchronize(self):
-        self._all("synchronize")
-
-    def get_compute_num(self):
-        return self.slabs[0].get_compute_num()
-
-    def read_population(self, k, buffer=-1):
-        return np.concatenate(self._all("read_population", k, buffer), axis=0)
-
-    def read_moments(self):
-        parts = self._all("read_moments")
-        return tuple(np.concatenate([p[q] for p in parts], axis=0) for q in range(3))
-
-    def read_output(self):
-        return np.concatenate(self._all("read_output"), axis=0)
-
-    def read_barrier(self):
-        return np.concatenate(self._all("read_barrier"), axis=0)
-
-    def read_cell_class(self):
-        return np.concatenate(self._all("read_cell_class"), axis=0)
+    def group_size(self):
+        return int(self._L.blbm_group_size(self._h))

@@ -35,6 +35,10 @@ extern "C" {
     pub fn blbm_create(w: u32, h: u32, omega: c_float, inflow_ux: c_float, device: c_int, out: *mut *mut blbm_t) -> c_int;
     pub fn blbm_create_slab(w: u32, h_global: u64, row_begin: u64, row_end: u64, omega: c_float, inflow_ux: c_float,
                             device: c_int, out: *mut *mut blbm_t) -> c_int;
+    pub fn blbm_create_group(w: u32, h: u64, omega: c_float, inflow_ux: c_float, devices: *const c_int, ndev: c_int,
+                             out: *mut *mut blbm_t) -> c_int;
+    pub fn blbm_group_size(h: *const blbm_t) -> c_int;
+    pub fn blbm_group_slab(h: *mut blbm_t, index: c_int, slab: *mut *mut blbm_t) -> c_int;
     pub fn blbm_destroy(h: *mut blbm_t) -> c_int;
     pub fn blbm_iterate(h: *mut blbm_t, n: u32) -> c_int;
     pub fn blbm_advance(h: *mut blbm_t, n: u32) -> c_int;

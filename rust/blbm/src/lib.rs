@@ -15,10 +15,19 @@ pub enum SummaryStat {
     Speed = 4,
 }
 
-/// Stand-in for lbm-wgpu's `Driver` (driver.rs:1-7): the CUDA device and stream live inside the handle.
-#[derive(Default, Clone, Copy)]
+/// Stand-in for lbm-wgpu's `Driver` (driver.rs:1-7): the CUDA devices and streams live inside the handle.
+/// One device: the whole lattice on it.  Several: `LBM::new` cuts the lattice into y-slabs, one per listed
+/// device, behind the same `LBM` value (blbm_create_group), so a 65536 x 65536 lattice is constructed with
+/// `Driver { devices: (0..8).collect() }` and stepped, painted and read exactly like a small one.
+#[derive(Clone)]
 pub struct Driver {
-    pub device: i32,
+    pub devices: Vec<i32>,
+}
+
+impl Default for Driver {
+    fn default() -> Driver {
+        Driver { devices: vec![0] }
+    }
 }
 
 /// `trait Shape` of barrier_shapes/mod.rs:11-19, reduced to what draw_shape needs.
@@ -45,7 +54,9 @@ impl LBM {
     /// lbm.rs:726
     pub fn new(driver: &Driver, omega: f32, x: u32, y: u32) -> LBM {
         let mut h = std::ptr::null_mut();
-        check(unsafe { sys::blbm_create(x, y, omega, 0.1, driver.device, &mut h) });
+        check(unsafe {
+            sys::blbm_create_group(x, y as u64, omega, 0.1, driver.devices.as_ptr(), driver.devices.len() as i32, &mut h)
+        });
         LBM { h, x, y, compute_step: 0 }
     }
     /// lbm.rs:1065 (minus colour map and render)

@@ -45,12 +45,14 @@ static void expect_bits(const std::vector<float> &got, const float *want, const 
     }
 }
 
+static void run(const blbm::Driver &driver, const char *label);
+
 int main(int argc, char **argv)
 {
     using namespace blbm;
-    const Driver driver;
     if (argc > 1 && std::string(argv[1]) == "--no-gpu") {
         try {
+            const Driver driver;
             LBM lbm(driver, 1.25f, 64, 32);
         } catch (const Error &e) {
             printf("constructing without a GPU failed as it must: %s\n", e.what());
@@ -59,7 +61,20 @@ int main(int argc, char **argv)
         printf("a GPU is present\n");
         return 0;
     }
+    run(Driver(), "one device");
+    // the same LBM value over three y-slabs (blbm_create_group): distinct GPUs when the box has them, else three
+    // slabs on device 0 — either way the halo rows travel by direct stores from the step kernel
+    const int ndev = blbm_device_count();
+    std::vector<int> devs;
+    for (int q = 0; q < 3; q++) devs.push_back(ndev >= 3 ? q : 0);
+    run(Driver(devs), "three slabs");
+    printf(failures ? "FAILED (%d)\n" : "ok: blbm::LBM bit-identical to the oracle (%d failures)\n", failures);
+    return failures ? 1 : 0;
+}
 
+static void run(const blbm::Driver &driver, const char *label)
+{
+    using namespace blbm;
     const uint32_t x = 320, y = 96;
     const float omega = 1.0f / (3.0f * 0.02f + 0.5f);  // lib.rs:183
     LBM lbm(driver, omega, x, y);
@@ -74,22 +89,23 @@ int main(int argc, char **argv)
         }
         lbm_oracle_draw_points(ora, pairs.data(), pairs.size() / 2);
     };
-    auto compare = [&](const char *tag) {
+    auto compare = [&](const char *what) {
+        const std::string tag = std::string(label) + ": " + what;
         for (int b = 0; b < 2; b++)
             for (int k = 0; k < 9; k++)
                 expect_bits(lbm.read_population(k, b), lbm_oracle_population(ora, k == 4 ? 0 : b, k),
-                            (std::string(tag) + " population " + std::to_string(b) + "/" + std::to_string(k)).c_str());
-        expect_bits(lbm.read_output(), lbm_oracle_output(ora), (std::string(tag) + " output").c_str());
+                            (tag + " population " + std::to_string(b) + "/" + std::to_string(k)).c_str());
+        expect_bits(lbm.read_output(), lbm_oracle_output(ora), (tag + " output").c_str());
         std::vector<float> rgb((size_t)x * y * 3);
         lbm_oracle_color_map(ora, (int)lbm.color_map, rgb.data());
-        expect_bits(lbm.read_colors(), rgb.data(), (std::string(tag) + " colours").c_str());
+        expect_bits(lbm.read_colors(), rgb.data(), (tag + " colours").c_str());
         const std::vector<uint32_t> bar = lbm.read_barrier();
         if (memcmp(bar.data(), lbm_oracle_barrier(ora), bar.size() * 4) != 0) {
-            printf("FAIL %s barrier\n", tag);
+            printf("FAIL %s barrier\n", tag.c_str());
             failures++;
         }
         if (lbm.get_compute_num() != lbm_oracle_compute_num(ora)) {
-            printf("FAIL %s compute_num\n", tag);
+            printf("FAIL %s compute_num\n", tag.c_str());
             failures++;
         }
     };
@@ -97,8 +113,11 @@ int main(int argc, char **argv)
     // the call pattern of lib.rs:108-199: paint, iterate(15), change viscosity, erase, switch output
     Line l1, l2;
     std::string err;
-    if (!Line::make(&l1, {60, 20}, {60, 70}, x, y) || !Line::make(&l2, {120, 30}, {200, 60}, x, y)) return 3;
-    if (Line::make(&l1, {60, 20}, {(int64_t)x, 70}, x, y, false, &err)) return 4;  // Err, like Line::new
+    if (!Line::make(&l1, {60, 20}, {60, 70}, x, y) || !Line::make(&l2, {120, 30}, {200, 60}, x, y)) {
+        failures++;
+        return;
+    }
+    if (Line::make(&l1, {60, 20}, {(int64_t)x, 70}, x, y, false, &err)) failures++;  // Err, like Line::new
     Line::make(&l1, {60, 20}, {60, 70}, x, y);
     both_draw(l1);
     for (int frame = 0; frame < 20; frame++) {
@@ -131,6 +150,4 @@ int main(int argc, char **argv)
     lbm_oracle_iterate(ora, 40);
     compare("after custom_speed/reset_barrier");
     lbm_oracle_destroy(ora);
-    printf(failures ? "FAILED (%d)\n" : "ok: blbm::LBM bit-identical to the oracle (%d failures)\n", failures);
-    return failures ? 1 : 0;
 }

@@ -148,9 +148,9 @@ def test_every_entry_point_rejects_a_null_handle_without_crashing():
     or the neutral value for the plain getters — sets blbm_last_error, and never dereferences the handle."""
     lib = lbm_b200.load_library()
     getters = {"blbm_get_compute_num": 0, "blbm_get_frame_num": 0, "blbm_get_launch_count": 0,
-               "blbm_get_device_bytes": 0, "blbm_get_lazy_barriers_active": 0}
+               "blbm_get_device_bytes": 0, "blbm_get_lazy_barriers_active": 0, "blbm_group_size": 0}
     no_handle = {"blbm_last_error", "blbm_abi_version", "blbm_device_count", "blbm_create", "blbm_create_slab",
-                 "blbm_rasterize_line"}
+                 "blbm_create_group", "blbm_rasterize_line"}
     checked = 0
     for name, (res, args) in host.PROTOTYPES.items():
         if name in no_handle:
@@ -172,6 +172,10 @@ def test_every_entry_point_rejects_a_null_handle_without_crashing():
     assert lib.blbm_create(0, 8, 1.0, 0.1, 0, C.byref(h)) < 0 and not h
     assert lib.blbm_create_slab(8, 8, 4, 4, 1.0, 0.1, 0, C.byref(h)) < 0 and not h
     assert lib.blbm_create(8, 8, 1.0, 0.1, 0, None) < 0
+    devs = (C.c_int * 2)(0, 0)
+    assert lib.blbm_create_group(8, 8, 1.0, 0.1, None, 2, C.byref(h)) < 0 and not h
+    assert lib.blbm_create_group(8, 8, 1.0, 0.1, devs, 0, C.byref(h)) < 0 and not h
+    assert lib.blbm_create_group(8, 3, 1.0, 0.1, devs, 2, C.byref(h)) < 0 and not h  # fewer than 2 rows per slab
 
 
 def test_header_is_plain_c():

@@ -35,7 +35,11 @@ def _scenario(w, h):
     return [(p1, 33), (p2, 20), (None, 1), (None, 14)]
 
 
-def _worker(rank, world, port, w, h, kernel, lazy, out_dir):
+_RESETS = [("custom_speed", 0.07, 12), ("single_cell", 5, 9), ("single_cell", 4, 3), ("custom_speed", 0.1, 1),
+           ("single_cell", 3, 21)]
+
+
+def _worker(rank, world, port, w, h, kernel, lazy, out_dir, resets=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -57,6 +61,12 @@ def _worker(rank, world, port, w, h, kernel, lazy, out_dir):
             if pairs is not None:
                 lbm.draw_points(pairs)
             lbm.iterate(steps)
+        if resets:
+            # resets are collective: each slab refills its own halo rows, and no neighbour's next launch may store
+            # into them before that fill ran (the ranks drift freely here); single_cell 3..5 sit on y/2
+            for op, arg, steps in _RESETS:
+                getattr(lbm, op)(arg)
+                lbm.iterate(steps)
         res = {f"f{b}_{k}": lbm.read_population(k, b) for b in (0, 1) for k in range(9)}
         mx, my, rho = lbm.read_moments()
         res.update(mx=mx, my=my, rho=rho, out=lbm.read_output(), bar=lbm.read_barrier(), cls=lbm.read_cell_class())
@@ -92,3 +102,31 @@ def test_ipc_linked_slabs_match_oracle(world, kernel, lazy, tmp_path):
     assert_same_bits(cat("out"), o.output(), "curl output")
     assert_same_bits(cat("bar"), o.barrier(), "barrier")
     assert_same_bits(cat("cls"), o.cell_class(), "class")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ipc_linked_slabs_resets_are_ordered_against_neighbour_pushes(world, tmp_path):
+    """custom_speed / single_cell on linked slabs of independent processes, each followed by iterate: the refill of
+    a slab's halo rows is published through the epoch handshake, so a neighbour that is already past its own reset
+    cannot have its first halo stores overwritten by our fill."""
+    from oracle.lbm_oracle import Oracle
+    from tests.util import assert_same_bits
+    w, h = 160, 46
+    mp.spawn(_worker, args=(world, _free_port(), w, h, 2, 1, str(tmp_path), True), nprocs=world, join=True)
+    o = Oracle(1.0 / (3 * 0.02 + 0.5), w, h)
+    for pairs, steps in _scenario(w, h):
+        if pairs is not None:
+            o.draw_points(pairs.astype(np.uint32))
+        o.iterate(steps)
+    for op, arg, steps in _RESETS:
+        getattr(o, op)(arg)
+        o.iterate(steps)
+    parts = [np.load(os.path.join(str(tmp_path), f"rank{r}.npz")) for r in range(world)]
+    cat = lambda name: np.concatenate([p[name] for p in parts], axis=0)  # noqa: E731
+    for b in (0, 1):
+        for k in range(9):
+            assert_same_bits(cat(f"f{b}_{k}"), o.population(b, k), f"population[{b}][{k}]")
+    omx, omy, orho = o.moments()
+    assert_same_bits(cat("mx"), omx, "mx")
+    assert_same_bits(cat("rho"), orho, "rho")
+    assert_same_bits(cat("out"), o.output(), "curl output")

@@ -540,3 +540,110 @@ def test_api_fuzz_slab_group(seed):
     grp = SlabGroup(om, w, h, devices=[0] * nslabs, kernel=Kernel(int(rng.integers(1, 4))),
                     lazy_barriers=int(rng.integers(0, 3)))
     _fuzz(grp, Oracle(om, w, h), rng, w, h, f"slab fuzz seed {seed} x{nslabs}", tunable=False, nops=80)
+
+
+def _group_devices(n):
+    """distinct GPUs when the box has them (first hardware path of blbm_link_local across devices), else n slabs
+    on cuda:0"""
+    from lbm_b200 import load_library
+    ndev = load_library().blbm_device_count()
+    return list(range(n)) if ndev >= n else [0] * n
+
+
+@pytest.mark.parametrize("nslabs", [2, 3, 5])
+def test_group_handle_spans_the_whole_api(nslabs):
+    """blbm_create_group: ONE handle over n linked slabs.  Everything a caller of the reference's `LBM` does —
+    presets, line strokes, colour maps, resets, half-steps, checkpoint/restore, timers, reductions — goes through
+    the same C entry points as on one device and stays bit-identical to the oracle."""
+    import ctypes as C
+    from lbm_b200.lbm import _check, _P, slab_rows
+    from oracle import barrier_shapes
+    w, h = 200, 61
+    om = omega_from_viscosity(0.03)
+    grp = LBM(om, w, h, devices=_group_devices(nslabs), kernel=Kernel.Vec4)
+    ora = Oracle(om, w, h)
+    L = grp._L
+    assert L.blbm_group_size(grp._h) == nslabs
+    # geometry: the group is the whole lattice, its slabs the contiguous row ranges
+    for q, (r0, r1) in enumerate(slab_rows(h, nslabs)):
+        s = _P()
+        _check(L.blbm_group_slab(grp._h, q, C.byref(s)))
+        ww, hg, a, b, dev = C.c_uint32(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        _check(L.blbm_get_geometry(s, C.byref(ww), C.byref(hg), C.byref(a), C.byref(b), C.byref(dev)))
+        assert (ww.value, hg.value, a.value, b.value) == (w, h, r0, r1)
+    assert L.blbm_group_slab(grp._h, nslabs, C.byref(_P())) < 0
+    buf = C.create_string_buffer(512)
+    assert L.blbm_export_peer(grp._h, buf) == -5  # BLBM_ESTATE: groups link themselves
+    # a stroke across every slab boundary through the host rasteriser, then the frame loop
+    pts = barrier_shapes.line_points((30, 3), (150, 57), w, h)
+    grp.draw_line((30, 3), (150, 57))
+    ora.draw_points(np.array([[px + py * w, 1] for px, py, *_ in pts], np.uint32))
+    t = grp.iterate_timed(70)  # more than two interleaving chunks of 32
+    assert t > 0
+    ora.iterate(70)
+    compare_state(grp, ora, f"group x{nslabs} after 70 steps")
+    for stat in (SummaryStat.Speed, SummaryStat.Rho, SummaryStat.Curl):
+        grp.compute_summary(stat)
+        ora.compute_summary(int(stat))
+        assert_same_bits(grp.read_output(), ora.output(), f"group stat {stat.name}")
+    grp.color_map(2)
+    assert_same_bits(grp.read_colors(), np.asarray(ora.color_map(2)).reshape(h, w, 3), "group colours")
+    # checkpoint / restore through the group handle, then half-steps and resets in lock-step
+    saved = [[grp.read_population(k, b) for k in range(9)] for b in (0, 1)]
+    grp.iterate(10)  # an even number of steps: the restored buffers keep their roles (compute_step parity)
+    for b in (0, 1):
+        for k in range(9):
+            grp.write_population(k, saved[b][k], b)
+    grp.collide(); ora.collide()
+    grp.stream(); ora.stream()
+    grp.iterate(5); ora.iterate(5)
+    for b in (0, 1):
+        for k in range(9):
+            assert_same_bits(grp.read_population(k, b), ora.population(b, k), f"group restore pop[{b}][{k}]")
+    for idx in (5, 4, 1):  # single_cell 3..5 sit on the slab boundary of a 2-slab split
+        grp.single_cell(idx); ora.single_cell(idx)
+        grp.iterate(7); ora.iterate(7)
+        compare_state(grp, ora, f"group single_cell {idx}")
+    grp.custom_speed(0.06); ora.custom_speed(0.06)
+    grp.iterate(33); ora.iterate(33)
+    compare_state(grp, ora, "group custom_speed")
+    s_rho, s_mx, s_my, mabs = grp.reduce_moments()
+    omx, omy, orho = ora.moments()
+    assert abs(s_rho - float(np.sum(orho, dtype=np.float64))) < 1e-6 * abs(s_rho)
+    assert mabs == float(np.abs(ora.output()).max())
+    assert grp.launch_count() > 0 and grp.device_bytes() > 0
+    grp.close()
+
+
+def test_group_of_one_device_is_a_plain_handle():
+    grp = LBM(1.25, 64, 32, devices=[0])
+    assert grp._L.blbm_group_size(grp._h) == 1
+    ora = Oracle(1.25, 64, 32)
+    grp.iterate(10); ora.iterate(10)
+    compare_state(grp, ora, "group of one")
+    grp.close()
+
+
+def test_paint_frames_never_synchronise_and_stay_exact():
+    """The frame loop of lib.rs:108-199 — paint a stroke, iterate(n), read the field back asynchronously — with
+    more paints in flight than the pinned staging ring has slots, and one list longer than a slot."""
+    import torch
+    w, h = 256, 96
+    om = omega_from_viscosity(0.02)
+    lbm, ora = LBM(om, w, h), Oracle(om, w, h)
+    rng = np.random.default_rng(5)
+    outs = [torch.empty((h, w), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    for fr in range(12):
+        n = 9000 if fr == 6 else int(rng.integers(1, 200))  # frame 6 exceeds the 8192-pair slot
+        loc = rng.integers(w, w * (h - 1), size=n)
+        val = rng.integers(0, 2, size=n)
+        pairs = np.stack([loc, val], 1).astype(np.uint32)
+        lbm.draw_points(pairs)
+        pairs[:] = 0xFFFFFFFF  # the caller's buffer is free again on return
+        ora.draw_points(np.stack([loc, val], 1).astype(np.uint32))
+        lbm.iterate(3); ora.iterate(3)
+        lbm.read_output_async(outs[fr & 1].data_ptr())
+    lbm.synchronize()
+    assert_same_bits(outs[1].numpy(), ora.output(), "async output of the last frame")
+    compare_state(lbm, ora, "after 12 pipelined paint frames")
+    lbm.close()
