@@ -193,8 +193,26 @@ class LBM:
     # -- life cycle
     def close(self):
         if getattr(self, "_h", None):
-            self._L.blbm_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._L.blbm_destroy(self._h)
             self._h = None
+
+    def group_size(self):
+        """number of slabs behind the handle (1 unless created with devices=[...])"""
+        return int(self._L.blbm_group_size(self._h))
+
+    def slab(self, index):
+        """Non-owning view of slab `index` of a group handle (per-slab geometry, mask windows, tuning).  Calls that
+        step or exchange halos belong on the group, which keeps its slabs in lock-step."""
+        h = _P()
+        _check(self._L.blbm_group_slab(self._h, int(index), C.byref(h)))
+        v = object.__new__(LBM)
+        v._L, v._h, v._owned = self._L, h, False
+        w, hg, a, b, dev = _U32(), _U64(), _U64(), _U64(), _I()
+        _check(self._L.blbm_get_geometry(h, C.byref(w), C.byref(hg), C.byref(a), C.byref(b), C.byref(dev)))
+        v.x, v.y, v.row_begin, v.row_end, v.device = w.value, hg.value, a.value, b.value, dev.value
+        v.summary_stat = self.summary_stat
+        return v
 
     def __del__(self):
         try:
@@ -446,6 +464,3 @@ class SlabGroup(LBM):
         super().__init__(omega, x, y, inflow_ux=inflow_ux, kernel=kernel, lazy_barriers=lazy_barriers,
                          devices=list(devices))
         self.ranges = slab_rows(y, len(devices))
-
-    def group_size(self):
-        return int(self._L.blbm_group_size(self._h))
