@@ -320,7 +320,7 @@ class Job:
         from lbm_b200 import LBM, Kernel
         from lbm_b200.lbm import slab_rows
         args = self.args
-        kernel = {"auto": Kernel.Auto, "scalar": Kernel.Scalar, "vec4": Kernel.Vec4, "tma": Kernel.Tma}[args.kernel]
+        kernel = {"auto": Kernel.Auto, "scalar": Kernel.Scalar, "vec4": Kernel.Vec4}[args.kernel]
         lazy = None if args.lazy < 0 else args.lazy
         idx, cnt = part if part is not None else (self.rank, self.world)
         if self.single and part is None and self.ngpu > 1:
@@ -343,9 +343,8 @@ class Job:
             mr0, m = mask_rows(kind, w, h_total, r0 - 2, r1 + 2, discs)
             lbm.write_barrier_rows(mr0, m)
             del m
-        for knob, val in ((0, args.block_rows), (1, args.tma_rows), (2, args.tma_stages), (3, args.tma_ctas)):
-            if val:
-                lbm.set_tuning(knob, val)
+        if args.block_rows:
+            lbm.set_tuning(0, args.block_rows)
         for knob, val in ((4, args.dense), (5, args.graphs), (6, args.packed), (7, args.index32)):
             if val >= 0:
                 lbm.set_tuning(knob, val)
@@ -575,7 +574,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=15)
     ap.add_argument("--impl", default="blbm", choices=["blbm", "reference"])
     ap.add_argument("--workload", default="porous16384", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "scalar", "vec4", "tma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "scalar", "vec4"])
     ap.add_argument("--single-process", action="store_true",
                     help="one process drives all --gpus devices through one blbm_create_group handle")
     ap.add_argument("--frame-steps", type=int, default=15, help="steps per frame of the e2e loop (lib.rs:17)")
@@ -584,9 +583,6 @@ def main():
     ap.add_argument("--dense", type=int, default=-1, help="vec4 bounce flavour: -1 auto, 0 sparse, 1 dense, 2 dense + cp.async staging")
     ap.add_argument("--packed", type=int, default=-1, help="vec4 packed fp32 adds (FADD2): -1 default (off: measured slower), 0, 1")
     ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 auto, 0, 1")
-    ap.add_argument("--tma-rows", type=int, default=0)
-    ap.add_argument("--tma-stages", type=int, default=0)
-    ap.add_argument("--tma-ctas", type=int, default=0)
     ap.add_argument("--lazy", type=int, default=-1, help="barrier-chain table: 0 never, 1 always, 2 auto (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -58,8 +58,11 @@ typedef enum blbm_pop {
 typedef enum blbm_kernel {
     BLBM_KERNEL_AUTO = 0,
     BLBM_KERNEL_SCALAR = 1, /* one cell per thread, 32-bit accesses */
-    BLBM_KERNEL_VEC4 = 2,   /* four cells per thread, 128-bit accesses, shuffle-realigned x+-1 gathers */
-    BLBM_KERNEL_TMA = 3     /* persistent CTAs, TMA (cp.async.bulk.tensor) staged tiles, mbarrier ring */
+    BLBM_KERNEL_VEC4 = 2    /* four cells per thread, 128-bit accesses, shuffle-realigned x+-1 gathers, the
+                               bounce-back's own rows staged in shared memory with cp.async (default) */
+    /* 3 was a TMA-staged variant (persistent CTAs, cp.async.bulk.tensor tiles behind an mbarrier ring): bit-identical
+       but 0.72-0.80 of the HBM peak against 0.95-1.0 for VEC4 on every workload (profiles/r1/tma_ab_*.json,
+       ncu_step_tma_channel16384.txt) — retired in round 2; blbm_set_kernel(3) fails with BLBM_EINVAL */
 } blbm_kernel;
 
 #define BLBM_PEER_HANDLE_BYTES 512
@@ -242,9 +245,7 @@ int blbm_get_kernel(const blbm_t *h);       /* the resolved implementation (neve
 /* launch-shape knobs for A/B measurement; results never depend on them */
 typedef enum blbm_tune {
     BLBM_TUNE_VEC4_BLOCK_ROWS = 0, /* rows of 128 cells per block: 1, 2, 4 (default), 8, 16 */
-    BLBM_TUNE_TMA_TILE_ROWS = 1,   /* rows per TMA tile: 4 (default) or 8 */
-    BLBM_TUNE_TMA_STAGES = 2,      /* depth of the shared-memory ring: 2..4 (default 4) */
-    BLBM_TUNE_TMA_CTAS_PER_SM = 3, /* persistent CTAs per SM: 1..8 (default 2) */
+    /* 1..3 belonged to the retired TMA-staged kernel */
     BLBM_TUNE_VEC4_DENSE = 4,      /* bounce-back fix-up flavour: -1 auto (default), 0 sparse, 1 dense obstacles,
                                       2 dense + own-row vectors staged in shared memory with cp.async (what auto
                                       picks wherever the barrier-chain table is active), 3 as 2 with the class

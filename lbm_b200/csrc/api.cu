@@ -225,10 +225,6 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     cudaError_t e;
     switch (k) {
     case BLBM_KERNEL_SCALAR: e = launch_step_scalar(p, mode, mom, h->stream); break;
-    case BLBM_KERNEL_TMA:
-        e = launch_step_tma(p, mode, mom, h->tma_maps, h->tma_map_rest, xbuf, h->tma_rows, h->tma_stages, h->tma_ctas,
-                            h->stream);
-        break;
     default:
         // the obstacle-dense flavour with cp.async-staged own rows wherever the chain table is in use (>= 2 % barrier
         // cells), unless overridden
@@ -286,7 +282,7 @@ constexpr uint32_t GRAPH_CHUNK = 8;  // even, so a replay starts on the parity i
 
 bool graphs_wanted(const blbm *h)
 {
-    if (any_peer(h) || h->kernel == BLBM_KERNEL_TMA) return false;  // peers: per-step handshake kernels
+    if (any_peer(h)) return false;  // peers: per-step handshake kernels
     if (h->use_graphs >= 0) return h->use_graphs != 0;
     return (unsigned long long)h->rows * h->W <= (4ull << 20);
 }
@@ -684,7 +680,6 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     CK(cudaSetDevice(device));
     CK(preload_aux_kernels());
     CK(preload_step_kernels());
-    CK(preload_tma_kernels());
 
     blbm *h = new (std::nothrow) blbm();
     if (!h) return fail(BLBM_ENOMEM, "out of host memory");
@@ -1374,15 +1369,6 @@ int blbm_exchange_halos(blbm_t *h)
     return push_all_halos(h);
 }
 
-static int tma_prepare(blbm *h)
-{
-    if (!tma_available()) return fail(BLBM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    if (!tma_encode_planes(h->tma_maps, h->f, h->R, h->tma_map_rest, h->P, h->rows + 3, h->tma_rows))
-        return fail(BLBM_ECUDA, "encoding the TMA tensor maps failed");
-    h->tma_ready = true;
-    return BLBM_OK;
-}
-
 int blbm_set_kernel(blbm_t *h, int kernel)
 {
     GRP_EACH(h, blbm_set_kernel(s, kernel));
@@ -1391,14 +1377,6 @@ int blbm_set_kernel(blbm_t *h, int kernel)
     case BLBM_KERNEL_AUTO: h->kernel = BLBM_KERNEL_VEC4; break;
     case BLBM_KERNEL_SCALAR:
     case BLBM_KERNEL_VEC4: h->kernel = kernel; break;
-    case BLBM_KERNEL_TMA: {
-        if (!h->tma_ready) {
-            int rc = tma_prepare(h);
-            if (rc) return rc;
-        }
-        h->kernel = kernel;
-        break;
-    }
     default: return fail(BLBM_EINVAL, "kernel %d not available", kernel);
     }
     return BLBM_OK;
@@ -1431,22 +1409,6 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
     case BLBM_TUNE_CUDA_GRAPHS:
         if (value < -1 || value > 1) return fail(BLBM_EINVAL, "graphs must be -1 (auto), 0 or 1");
         h->use_graphs = value;
-        return BLBM_OK;
-    case BLBM_TUNE_TMA_TILE_ROWS:
-        if (value != 4 && value != 8) return fail(BLBM_EINVAL, "TMA tile rows must be 4 or 8");
-        if (value != h->tma_rows) {
-            h->tma_rows = value;
-            h->tma_ready = false;  // the boxes are part of the tensor maps
-            if (h->kernel == BLBM_KERNEL_TMA) return tma_prepare(h);
-        }
-        return BLBM_OK;
-    case BLBM_TUNE_TMA_STAGES:
-        if (value < 2 || value > 4) return fail(BLBM_EINVAL, "TMA stages must be 2, 3 or 4");
-        h->tma_stages = value;
-        return BLBM_OK;
-    case BLBM_TUNE_TMA_CTAS_PER_SM:
-        if (value < 1 || value > 8) return fail(BLBM_EINVAL, "TMA CTAs per SM must be 1..8");
-        h->tma_ctas = value;
         return BLBM_OK;
     default: return fail(BLBM_EINVAL, "unknown tuning knob %d", knob);
     }

@@ -258,7 +258,6 @@ enum StepMode { MODE_FUSED = 0, MODE_COLLIDE_ONLY = 1, MODE_STREAM_ONLY = 2 };
 // force the lazy module load of every kernel of the library (see aux_kernels.cu)
 cudaError_t preload_aux_kernels();
 cudaError_t preload_step_kernels();
-cudaError_t preload_tma_kernels();
 
 // launchers (kernels.cu)
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
@@ -266,14 +265,6 @@ cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments
 // index32: use 32-bit plane offsets where the slab allows it
 cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, int dense_obstacles,
                              bool packed, bool index32, cudaStream_t st);
-
-// TMA-staged variant (tma_kernel.cu).  The tensor maps are opaque 128-byte blobs owned by the handle:
-// 16 population maps (buffer-major, Dir order) and one for the rest plane, encoded for `tile_rows`.
-bool tma_available();
-bool tma_encode_planes(void *maps16x128, float *const f[2][8], const float *R, void *mapR, uint32_t P,
-                       uint32_t dev_rows, int tile_rows);
-cudaError_t launch_step_tma(const StepParams &p, int mode, bool store_moments, const void *maps16x128,
-                            const void *mapR, int xbuf, int tile_rows, int stages, int ctas_per_sm, cudaStream_t st);
 
 // ---- auxiliary kernels (aux_kernels.cu) ----------------------------------------------------------
 // Slab geometry shared by the auxiliary launchers.  Population/moment/class planes have rows+3 device

@@ -92,11 +92,6 @@ struct blbm_handle {
     int vec4_packed = 0;  // 1: collide cell pairs with packed fp32 adds (FADD2): same bits, but measured slower (registers)
     int vec4_index32 = -1;  // 32-bit plane offsets in the vec4 kernel (plane < 2^32 elements): -1 auto, 0, 1
     int vec4_rows = 4;  // rows per block of the vec4 kernel (tuning knob; 4 measured best on the porous case)
-    // TMA-staged kernel: tensor maps (opaque 128-byte descriptors) and launch shape
-    alignas(64) unsigned char tma_maps[16 * 128];
-    alignas(64) unsigned char tma_map_rest[128];
-    bool tma_ready = false;
-    int tma_rows = 4, tma_stages = 4, tma_ctas = 2;
     uint64_t launches = 0;
     blbmh::Peer up, dn;
     unsigned long long epoch = 0, waited = 0;

@@ -1,5 +1,5 @@
-// step_common.cuh — pieces shared by the four-cells-per-thread step kernels (register/shuffle gather in
-// kernels.cu, TMA-staged gather in tma_kernel.cu): everything after the gather of one group of four
+// step_common.cuh — the second half of the four-cells-per-thread step kernel (register/shuffle gather in
+// kernels.cu): everything after the gather of one group of four
 // consecutive cells — own-copy reload of skipped cells, the flat-index wrap at column W-1, collision,
 // stores, moments, halo mirroring.
 #pragma once

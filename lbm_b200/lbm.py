@@ -49,7 +49,6 @@ class Kernel(enum.IntEnum):
     Auto = 0
     Scalar = 1
     Vec4 = 2
-    Tma = 3
 
 
 class BlbmError(RuntimeError):

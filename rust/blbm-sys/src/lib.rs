@@ -20,9 +20,6 @@ pub const BLBM_PEER_HANDLE_BYTES: usize = 512;
 
 // blbm_tune (include/blbm.h): launch-shape knobs for A/B measurement; results never depend on them
 pub const BLBM_TUNE_VEC4_BLOCK_ROWS: c_int = 0;
-pub const BLBM_TUNE_TMA_TILE_ROWS: c_int = 1;
-pub const BLBM_TUNE_TMA_STAGES: c_int = 2;
-pub const BLBM_TUNE_TMA_CTAS_PER_SM: c_int = 3;
 pub const BLBM_TUNE_VEC4_DENSE: c_int = 4;
 pub const BLBM_TUNE_CUDA_GRAPHS: c_int = 5;
 pub const BLBM_TUNE_VEC4_PACKED: c_int = 6;

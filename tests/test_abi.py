@@ -116,8 +116,7 @@ def test_default_step_kernels_keep_their_register_budget_and_wide_accesses():
     use — step_vec4_kernel<no moments, 4 rows, flavour 0 | 2, scalar adds, 32-bit offsets> — must stay at
     64 registers without a spill (8 blocks of 128 threads per SM), move the populations with 128-bit global
     accesses, stage the bounce-back's own rows with cp.async (flavour 2), realign the x+-1 gathers with warp
-    shuffles; the TMA variant must really issue TMA loads behind mbarrier waits.  profiles/r1/sass_summary.txt
-    is the same table for every kernel of the library."""
+    shuffles.  profiles/r2/sass_summary.txt is the same table for every kernel of the library."""
     import importlib.util
     import shutil
     if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
@@ -138,8 +137,6 @@ def test_default_step_kernels_keep_their_register_budget_and_wide_accesses():
     for flavour in (0, 2):
         k = names[f"step_vec4_kernel<(bool)1, (int)4, (int){flavour}, (bool)0, u32>"]
         assert int(res[k]["REG"]) <= 80 and int(res[k]["STACK"]) == 0
-    tma = [k for n, k in names.items() if n.startswith("step_tma_kernel<")]
-    assert tma and all(counts[k]["UTMALDG"] >= 9 and counts[k]["SYNCS"] > 0 and int(res[k]["STACK"]) == 0 for k in tma)
 
 
 def test_every_entry_point_rejects_a_null_handle_without_crashing():
