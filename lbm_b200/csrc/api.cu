@@ -136,12 +136,23 @@ ChainPlanes chain_planes(const blbm *h)
     return pl;
 }
 
+ChainTable chain_table(const blbm *h)
+{
+    ChainTable t;
+    t.idx = h->chain_idx;
+    t.flag = h->chain_flag;
+    t.state = h->chain_state;
+    t.chunk_base = h->chunk_base;
+    t.n = h->chain_n;
+    t.cap = h->chain_cap;
+    return t;
+}
+
 // table -> planes: afterwards every barrier slot again holds exactly what the reference's buffers hold
 int chain_flush(blbm *h)
 {
     if (!h->chain_active) return BLBM_OK;
-    CK(launch_chain_flush(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, chain_planes(h), h->cls[0],
-                          h->cls[1], h->stream));
+    CK(launch_chain_flush(chain_table(h), chain_planes(h), h->cls[0], h->cls[1], (uint32_t)(h->step % 2), h->stream));
     h->launches++;
     h->chain_active = false;
     return BLBM_OK;
@@ -161,7 +172,7 @@ int chain_try_enter(blbm *h, uint32_t steps_left)
     if (h->chain_active || h->lazy_mode == 0 || h->chain_declined || h->cls_pending) return BLBM_OK;
     (void)steps_left;  // the build pays for itself within a few steps: enter as soon as the mask qualifies
     if (h->plane >= 0xffffffffull) return BLBM_OK;
-    CK(launch_chain_count(h->cls[h->cls_cur], geom(h), h->chain_counter, h->mailbox_dev, h->stream));
+    CK(launch_chain_count(h->cls[h->cls_cur], geom(h), h->chunk_base, h->chain_counter, h->mailbox_dev, h->stream));
     h->launches += 2;
     CK(cudaStreamSynchronize(h->stream));
     const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(h->mailbox_host);
@@ -172,25 +183,31 @@ int chain_try_enter(blbm *h, uint32_t steps_left)
     }
     if (h->chain_cap < n) {
         stream_free(h->chain_idx, h->stream);
+        stream_free(h->chain_flag, h->stream);
         stream_free(h->chain_state, h->stream);
         h->chain_idx = nullptr;
+        h->chain_flag = nullptr;
         h->chain_state = nullptr;
         h->chain_cap = 0;
         if (stream_alloc((void **)&h->chain_idx, n * sizeof(uint32_t), h->stream) != cudaSuccess ||
-            stream_alloc((void **)&h->chain_state, n * 17 * sizeof(float), h->stream) != cudaSuccess) {
+            stream_alloc((void **)&h->chain_flag, n, h->stream) != cudaSuccess ||
+            stream_alloc((void **)&h->chain_state, n * CHAIN_ROWS * sizeof(float), h->stream) != cudaSuccess) {
             cudaGetLastError();
             stream_free(h->chain_idx, h->stream);
+            stream_free(h->chain_flag, h->stream);
             h->chain_idx = nullptr;
+            h->chain_flag = nullptr;
             h->chain_declined = true;  // not enough memory: stay dense
             return BLBM_OK;
         }
         h->chain_cap = (size_t)n;
     }
-    CK(launch_chain_build(h->cls[h->cls_cur], h->cls[h->cls_cur ^ 1], geom(h), chain_planes(h), h->chain_idx,
-                          h->chain_state, h->chain_cap, h->chain_counter, h->stream));
-    h->launches++;
     h->chain_n = (size_t)n;
+    CK(launch_chain_build(h->cls[h->cls_cur], h->cls[h->cls_cur ^ 1], geom(h), chain_planes(h), chain_table(h),
+                          h->scan_scratch, (uint32_t)(h->step % 2), h->stream));
+    h->launches += 4;
     h->chain_active = true;
+    h->chain_unsettle = false;  // fresh entries carry no settled flag
     return BLBM_OK;
 }
 
@@ -223,6 +240,18 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     int k = h->kernel;
     if (mode != MODE_FUSED) k = BLBM_KERNEL_SCALAR;
     cudaError_t e;
+    if (mom && h->chain_active) {
+        // chain cells' moments (of the collide of buffer `ybuf`, which this launch performs for every other cell)
+        // live in the table: the vec4 kernel merges them by slot rank, the scalar kernel wants them in the planes
+        if (k == BLBM_KERNEL_SCALAR) {
+            CK(launch_chain_scatter_moments(chain_table(h), (uint32_t)ybuf, h->mx, h->my, h->rho, h->stream));
+            h->launches++;
+        } else {
+            p.chunk_base = h->chunk_base;
+            p.chain_mom = h->chain_state + (size_t)(CHAIN_ROW_MOM + 3 * ybuf) * h->chain_cap;
+            p.chain_cap = (uint32_t)h->chain_cap;
+        }
+    }
     switch (k) {
     case BLBM_KERNEL_SCALAR: e = launch_step_scalar(p, mode, mom, h->stream); break;
     default:
@@ -348,9 +377,10 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
         if (h->chain_active && !replayed) {
             // barrier cells do not depend on anything else: advance their chains through all the steps of
             // this call up front, in registers; this also stores the moments of the call's last collide
-            CK(launch_chain_replay(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, left,
-                                   (uint32_t)(h->step % 2), h->omega, h->mx, h->my, h->rho, h->stream));
+            CK(launch_chain_replay(chain_table(h), left, (uint32_t)(h->step % 2), h->omega, h->chain_unsettle,
+                                   h->stream));
             h->launches++;
+            h->chain_unsettle = false;
             replayed = true;
         }
         if (graphs && h->regimeT && !h->cls_pending && left > GRAPH_CHUNK) {
@@ -710,6 +740,8 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     const size_t off_cls0 = carve(h->plane * sizeof(uint16_t)), off_cls1 = carve(h->plane * sizeof(uint16_t));
     const size_t flag_bytes = (size_t)h->rows * ((h->P + CHUNK - 1) / CHUNK);
     const size_t off_rf0 = carve(flag_bytes), off_rf1 = carve(flag_bytes);
+    const size_t off_cb = carve(flag_bytes * sizeof(uint32_t));
+    const size_t off_ss = carve((flag_bytes / 1024 + 1) * sizeof(uint32_t));
     const size_t off_mask = carve((size_t)(h->rows + 4) * h->P);
     h->off_flags = carve(256);
     const size_t off_err = carve(64), off_red = carve(64), off_cnt = carve(64);
@@ -730,6 +762,8 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     h->cls[1] = reinterpret_cast<uint16_t *>(h->pool + off_cls1);
     h->rowflag[0] = reinterpret_cast<uint8_t *>(h->pool + off_rf0);
     h->rowflag[1] = reinterpret_cast<uint8_t *>(h->pool + off_rf1);
+    h->chunk_base = reinterpret_cast<uint32_t *>(h->pool + off_cb);
+    h->scan_scratch = reinterpret_cast<uint32_t *>(h->pool + off_ss);
     h->mask = reinterpret_cast<uint8_t *>(h->pool + off_mask);
     h->flags = reinterpret_cast<unsigned long long *>(h->pool + h->off_flags);
     h->err_flag = reinterpret_cast<int *>(h->pool + off_err);
@@ -807,6 +841,7 @@ int blbm_destroy(blbm_t *h)
         stream_free(h->rgb, h->stream);
         stream_free(h->d_pairs, h->stream);
         stream_free(h->chain_idx, h->stream);
+        stream_free(h->chain_flag, h->stream);
         stream_free(h->chain_state, h->stream);
         cudaStreamSynchronize(h->stream);
     }
@@ -942,6 +977,7 @@ int blbm_set_omega(blbm_t *h, float omega)
 {
     GRP_EACH(h, blbm_set_omega(s, omega));
     if (!h) return fail(BLBM_EINVAL, "null handle");
+    if (memcmp(&h->omega, &omega, sizeof(float)) != 0) h->chain_unsettle = true;  // settled chains hold for one omega
     h->omega = omega;
     return BLBM_OK;
 }
@@ -1039,9 +1075,9 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         }
         if (h->chain_active) {
             // cells about to change leave the chain table first (their state returns to the planes)
-            CK(launch_chain_evict(h->chain_idx, h->chain_state, h->chain_n, h->chain_cap, chain_planes(h),
-                                  h->cls[h->cls_cur], h->cls[h->cls_cur ^ 1], geom(h), h->d_pairs, nu, h->stream));
-            h->launches += 3;
+            CK(launch_chain_evict(chain_table(h), chain_planes(h), h->cls[h->cls_cur], h->cls[h->cls_cur ^ 1], geom(h),
+                                  h->d_pairs, nu, (uint32_t)(h->step % 2), h->stream));
+            h->launches++;
         }
         CK(launch_mask_scatter(h->mask, geom(h), h->d_pairs, nu, h->stream));
         h->launches++;

@@ -148,7 +148,7 @@ __global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const Sla
                     c = (uint16_t)((bar ? CLS_BARRIER : 0) | (skip ? CLS_SKIP : (uint16_t)up));
                     // cells whose state lives in the chain table stay there (a paint evicts the cells it
                     // touches before the mask changes, so a kept bit belongs to a cell that is still a barrier)
-                    if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & CLS_CHAIN;
+                    if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & (CLS_CHAIN | CLS_SLOT);
                 }
             }
             if (PUBLIC) {
@@ -454,22 +454,49 @@ cudaError_t launch_wait(const unsigned long long *from_up, const unsigned long l
 // collide the stale copy in buffer step%2 — in place, every step, sharing one rest population
 // (collision/*.wgsl have no mask test).  That is a closed 17-float recurrence per cell.  The chain
 // table holds those 17 floats compactly; chain_replay_kernel advances them n steps in registers with
-// the very same collide_cell() the step kernels use (bit-identical by construction) and stores the
-// moments of the last collide where the summary kernels expect them.
-// Layout: state[c*cap + e], c = 0..7 buffer-0 populations (Dir order), 8..15 buffer-1, 16 rest.
+// the very same collide_cell() the step kernels use (bit-identical by construction).
+//
+// The table is ORDERED by plane offset: the slot of a cell is chunk_base[row][chunk] plus the number of slot
+// bits (CLS_SLOT) in front of it inside its 128-cell chunk.  That makes every access of the replay coalesced —
+// including the moments of the latest collide, which stay in the table (rows CHAIN_ROW_MOM..) instead of being
+// scattered into the moment planes — lets the one moment-storing step launch of a call pick them up by rank,
+// and lets a paint find the slots of the cells it touches without scanning the table.
+//
+// Settled entries: once a two-step block (one collide of each copy) reproduces all 17 floats bit for bit, the
+// chain is on an exact period-2 cycle: both copies are fixed and the rest population alternates between two
+// values.  The table then holds both rest values and the moments of both collides, and the entry costs one flag
+// byte per call until omega changes.
 // ================================================================================================
 namespace blbmk {
 
-__global__ void chain_count_kernel(const uint16_t *cls, const SlabGeom g, unsigned long long *count)
+// class words of the four cells lane `lane` owns in chunk `chunk` of owned row r (zero beyond the pitch)
+__device__ __forceinline__ ushort4 chunk_words(const uint16_t *cls, const SlabGeom &g, uint32_t r, uint32_t chunk,
+                                               uint32_t lane, size_t *i0)
 {
+    const uint32_t x = chunk * CHUNK + lane * 4u;
+    *i0 = row_off(r, g.P) + x;
+    if (x >= g.P) return make_ushort4(0, 0, 0, 0);
+    return *reinterpret_cast<const ushort4 *>(cls + *i0);
+}
+
+// one warp per (row, chunk): barrier cells of the chunk -> chunk_cnt, grand total -> *count
+__global__ void chain_count_kernel(const uint16_t *cls, const SlabGeom g, uint32_t *chunk_cnt, unsigned long long *count)
+{
+    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
+    const size_t nwarps_total = (size_t)g.rows * nchunk;
+    const uint32_t lane = threadIdx.x & 31u;
     unsigned long long local = 0;
-    const size_t total = (size_t)g.rows * g.P;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (size_t)gridDim.x * blockDim.x)
-        local += (cls[(size_t)g.P + t] & CLS_BARRIER) ? 1u : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+    for (size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nwarps_total;
+         wid += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        size_t i0;
+        const ushort4 c = chunk_words(cls, g, (uint32_t)(wid / nchunk), (uint32_t)(wid % nchunk), lane, &i0);
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, count4(c, CLS_BARRIER));
+        if (lane == 0) {
+            chunk_cnt[wid] = sum;
+            local += sum;
+        }
+    }
+    if (lane == 0 && local) atomicAdd(count, local);
 }
 
 __global__ void mailbox_kernel(unsigned long long *host_mapped, const unsigned long long *src)
@@ -480,137 +507,210 @@ __global__ void mailbox_kernel(unsigned long long *host_mapped, const unsigned l
 
 // host_mailbox: mapped pinned host word the result is posted to by a store from the GPU — a D2H memcpy
 // would queue behind a large asynchronous read-back on the same copy engine
-cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, unsigned long long *count,
+cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, uint32_t *chunk_cnt, unsigned long long *count,
                                unsigned long long *host_mailbox, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    chain_count_kernel<<<148 * 8, 256, 0, st>>>(cls, g, count);
+    chain_count_kernel<<<148 * 8, 256, 0, st>>>(cls, g, chunk_cnt, count);
     mailbox_kernel<<<1, 1, 0, st>>>(host_mailbox, count);
     return cudaGetLastError();
 }
 
-__global__ void chain_build_kernel(uint16_t *cls, uint16_t *cls_other, const SlabGeom g, const ChainPlanes pl,
-                                   uint32_t *idx, float *state, size_t cap, unsigned long long *cursor)
+// ---- exclusive prefix sum of the per-chunk counts (three small kernels; tiles of 1024) ------------------
+constexpr uint32_t SCAN_TILE = 1024;
+
+// exclusive scan of up to 1024 values held four per thread by a 256-thread block; returns the block total
+__device__ __forceinline__ uint32_t block_excl_scan4(uint32_t (&v)[4], uint32_t *sh /* 8 words */)
 {
-    const size_t total = (size_t)g.rows * g.P;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = (size_t)g.P + t;  // plane offset of an owned cell (incl. pitch padding: class 0)
-        const uint16_t c = cls[i];
-        if (!(c & CLS_BARRIER)) continue;
-        const size_t e = (size_t)atomicAdd(cursor, 1ull);
-        if (e >= cap) continue;
-        cls[i] = c | CLS_CHAIN;
-        cls_other[i] |= CLS_CHAIN;  // the other class buffer may be stale elsewhere, but never about this bit
-        idx[e] = (uint32_t)i;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t wtotal;
+    const uint32_t in_warp = warp_excl_scan(mine, lane, &wtotal);
+    if (lane == 0) sh[warp] = wtotal;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
 #pragma unroll
-        for (int d = 0; d < 8; d++) {
-            state[(size_t)d * cap + e] = pl.f0[d][i];
-            state[(size_t)(8 + d) * cap + e] = pl.f1[d][i];
+    for (uint32_t w = 0; w < 8; w++) {
+        if (w < warp) before += sh[w];
+        total += sh[w];
+    }
+    __syncthreads();
+    uint32_t run = before + in_warp;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t t = v[q];
+        v[q] = run;
+        run += t;
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(256) scan_tiles_kernel(uint32_t *a, size_t m, uint32_t *tile_sums)
+{
+    __shared__ uint32_t sh[8];
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4u;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = base + q < m ? a[base + q] : 0u;
+    const uint32_t total = block_excl_scan4(v, sh);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (base + q < m) a[base + q] = v[q];
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// one block walks all tile sums (a few thousand at most) with a running carry
+__global__ void __launch_bounds__(256) scan_sums_kernel(uint32_t *sums, size_t t)
+{
+    __shared__ uint32_t sh[8];
+    uint32_t carry = 0;
+    for (size_t base = 0; base < t; base += SCAN_TILE) {
+        const size_t b = base + threadIdx.x * 4u;
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = b + q < t ? sums[b + q] : 0u;
+        const uint32_t total = block_excl_scan4(v, sh);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (b + q < t) sums[b + q] = v[q] + carry;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(uint32_t *a, size_t m, const uint32_t *tile_sums)
+{
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x * 4u;
+    const uint32_t add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (base + q < m) a[base + q] += add;
+}
+
+// one warp per (row, chunk): barrier cells -> consecutive slots, planes -> table
+__global__ void chain_fill_kernel(uint16_t *cls, uint16_t *cls_other, const SlabGeom g, const ChainPlanes pl,
+                                  const ChainTable t, const uint32_t parity)
+{
+    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
+    const size_t nwarps_total = (size_t)g.rows * nchunk;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nwarps_total;
+         wid += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        size_t i0;
+        const ushort4 c = chunk_words(cls, g, (uint32_t)(wid / nchunk), (uint32_t)(wid % nchunk), lane, &i0);
+        const uint32_t mine = count4(c, CLS_BARRIER);
+        uint32_t total;
+        uint32_t e = t.chunk_base[wid] + warp_excl_scan(mine, lane, &total);
+        if (total == 0) continue;
+        const uint16_t cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (!(cw[q] & CLS_BARRIER)) continue;
+            const size_t i = i0 + q;
+            if (e < t.cap) {
+                cls[i] = cw[q] | CLS_CHAIN | CLS_SLOT;
+                cls_other[i] |= CLS_CHAIN | CLS_SLOT;  // the other class buffer may be stale elsewhere, never about these bits
+                t.idx[e] = (uint32_t)i;
+                t.flag[e] = 0;
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    t.state[(size_t)d * t.cap + e] = pl.f0[d][i];
+                    t.state[(size_t)(8 + d) * t.cap + e] = pl.f1[d][i];
+                }
+                t.state[(size_t)(CHAIN_ROW_REST + parity) * t.cap + e] = pl.R[i];
+            }
+            e++;
         }
-        state[(size_t)16 * cap + e] = pl.R[i];
     }
 }
 
 cudaError_t launch_chain_build(uint16_t *cls, uint16_t *cls_other, const SlabGeom &g, const ChainPlanes &pl,
-                               uint32_t *idx, float *state, size_t cap, unsigned long long *cursor, cudaStream_t st)
+                               const ChainTable &t, uint32_t *scan_scratch, uint32_t parity, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
-    if (e != cudaSuccess) return e;
-    chain_build_kernel<<<148 * 8, 256, 0, st>>>(cls, cls_other, g, pl, idx, state, cap, cursor);
+    const size_t m = (size_t)g.rows * ((g.P + CHUNK - 1) / CHUNK);
+    const size_t tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    if (m == 0 || tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    scan_tiles_kernel<<<(unsigned)tiles, 256, 0, st>>>(t.chunk_base, m, scan_scratch);
+    scan_sums_kernel<<<1, 256, 0, st>>>(scan_scratch, tiles);
+    scan_add_kernel<<<(unsigned)tiles, 256, 0, st>>>(t.chunk_base, m, scan_scratch);
+    chain_fill_kernel<<<148 * 8, 256, 0, st>>>(cls, cls_other, g, pl, t, parity & 1u);
     return cudaGetLastError();
 }
 
-__device__ __forceinline__ void chain_store_entry(const float *state, size_t cap, size_t e, const ChainPlanes &pl,
-                                                  size_t i)
+// table -> planes for one entry; parity = buffer the NEXT collide acts on (its rest value is the current one)
+__device__ __forceinline__ void chain_store_entry(const ChainTable &t, size_t e, const ChainPlanes &pl, size_t i,
+                                                  uint32_t parity)
 {
 #pragma unroll
     for (int d = 0; d < 8; d++) {
-        pl.f0[d][i] = state[(size_t)d * cap + e];
-        pl.f1[d][i] = state[(size_t)(8 + d) * cap + e];
+        pl.f0[d][i] = t.state[(size_t)d * t.cap + e];
+        pl.f1[d][i] = t.state[(size_t)(8 + d) * t.cap + e];
     }
-    pl.R[i] = state[(size_t)16 * cap + e];
+    pl.R[i] = t.state[(size_t)(CHAIN_ROW_REST + parity) * t.cap + e];
 }
 
-__global__ void chain_flush_kernel(const uint32_t *idx, const float *state, size_t n, size_t cap,
-                                   const ChainPlanes pl, uint16_t *cls0, uint16_t *cls1)
+__global__ void chain_flush_kernel(const ChainTable t, const ChainPlanes pl, uint16_t *cls0, uint16_t *cls1,
+                                   const uint32_t parity)
 {
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t ie = idx[e];
-        if (ie == CHAIN_DEAD) continue;
-        const size_t i = ie;
-        chain_store_entry(state, cap, e, pl, i);
-        cls0[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
-        cls1[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < t.n; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = t.idx[e];
+        if (!(t.flag[e] & CHAIN_F_DEAD)) chain_store_entry(t, e, pl, i, parity);
+        cls0[i] &= (uint16_t)~(CLS_CHAIN | CLS_SLOT);
+        cls1[i] &= (uint16_t)~(CLS_CHAIN | CLS_SLOT);
     }
 }
 
-cudaError_t launch_chain_flush(const uint32_t *idx, const float *state, size_t n, size_t cap,
-                               const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1, cudaStream_t st)
+cudaError_t launch_chain_flush(const ChainTable &t, const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1,
+                               uint32_t parity, cudaStream_t st)
 {
-    if (n == 0) return cudaSuccess;
-    size_t nb = (n + 255) / 256;
+    if (t.n == 0) return cudaSuccess;
+    size_t nb = (t.n + 255) / 256;
     if (nb > 148 * 16) nb = 148 * 16;
-    chain_flush_kernel<<<(unsigned)nb, 256, 0, st>>>(idx, state, n, cap, pl, cls0, cls1);
+    chain_flush_kernel<<<(unsigned)nb, 256, 0, st>>>(t, pl, cls0, cls1, parity & 1u);
     return cudaGetLastError();
 }
 
 // ---- a paint touches some chain cells: move exactly those back into the planes ------------------------
-__device__ __forceinline__ bool pair_to_cell(const SlabGeom &g, uint64_t loc, size_t *i)
+// One warp per painted location: the slot is found by rank (chunk base + slot bits in front of the cell).
+__global__ void chain_evict_kernel(const ChainTable t, const ChainPlanes pl, uint16_t *cls_cur, uint16_t *cls_other,
+                                   const SlabGeom g, const uint64_t *pairs, size_t npairs, const uint32_t parity)
 {
-    const uint64_t gy = loc / g.W;
-    if (gy < g.row0 || gy >= g.row0 + g.rows) return false;
-    *i = row_off((uint32_t)(gy - g.row0), g.P) + (size_t)(loc - gy * g.W);
-    return true;
-}
-
-__global__ void chain_mark_kernel(uint16_t *cls, const SlabGeom g, const uint64_t *pairs, size_t npairs)
-{
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npairs;
-         t += (size_t)gridDim.x * blockDim.x) {
-        size_t i;
-        if (!pair_to_cell(g, pairs[2 * t], &i)) continue;
-        const uint16_t c = cls[i];
-        if (c & CLS_CHAIN) cls[i] = c | CLS_DIRTY;
+    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < npairs;
+         w += ((size_t)gridDim.x * blockDim.x) >> 5) {
+        const uint64_t loc = pairs[2 * w];
+        const uint64_t gy = loc / g.W;
+        if (gy < g.row0 || gy >= g.row0 + g.rows) continue;
+        const uint32_t r = (uint32_t)(gy - g.row0), x = (uint32_t)(loc - gy * g.W);
+        const size_t i = row_off(r, g.P) + x;
+        if (!(cls_cur[i] & CLS_CHAIN)) continue;  // warp-uniform
+        const uint32_t chunk = x / CHUNK;
+        size_t i0;
+        const ushort4 c = chunk_words(cls_cur, g, r, chunk, lane, &i0);
+        const uint16_t cw[4] = {c.x, c.y, c.z, c.w};
+        uint32_t before = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++)
+            if ((cw[q] & CLS_SLOT) && chunk * CHUNK + lane * 4u + q < x) before++;
+        const size_t e = (size_t)t.chunk_base[(size_t)r * nchunk + chunk] + __reduce_add_sync(0xffffffffu, before);
+        if (e >= t.n) continue;
+        if (lane < 8) pl.f0[lane][i] = t.state[(size_t)lane * t.cap + e];
+        else if (lane < 16) pl.f1[lane - 8][i] = t.state[(size_t)lane * t.cap + e];
+        else if (lane == 16) pl.R[i] = t.state[(size_t)(CHAIN_ROW_REST + parity) * t.cap + e];
+        else if (lane == 17) t.flag[e] = CHAIN_F_DEAD;
+        else if (lane == 18) cls_cur[i] &= (uint16_t)~CLS_CHAIN;
+        else if (lane == 19) cls_other[i] &= (uint16_t)~CLS_CHAIN;
     }
 }
 
-__global__ void chain_evict_kernel(uint32_t *idx, const float *state, size_t n, size_t cap, const ChainPlanes pl,
-                                   const uint16_t *cls)
+cudaError_t launch_chain_evict(const ChainTable &t, const ChainPlanes &pl, uint16_t *cls_cur, uint16_t *cls_other,
+                               const SlabGeom &g, const uint64_t *pairs, size_t npairs, uint32_t parity, cudaStream_t st)
 {
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t ie = idx[e];
-        if (ie == CHAIN_DEAD || !(cls[ie] & CLS_DIRTY)) continue;
-        chain_store_entry(state, cap, e, pl, ie);
-        idx[e] = CHAIN_DEAD;
-    }
-}
-
-__global__ void chain_unmark_kernel(uint16_t *cls_cur, uint16_t *cls_other, const SlabGeom g, const uint64_t *pairs,
-                                    size_t npairs)
-{
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npairs;
-         t += (size_t)gridDim.x * blockDim.x) {
-        size_t i;
-        if (!pair_to_cell(g, pairs[2 * t], &i)) continue;
-        cls_cur[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
-        cls_other[i] &= (uint16_t)~(CLS_CHAIN | CLS_DIRTY);
-    }
-}
-
-cudaError_t launch_chain_evict(uint32_t *idx, const float *state, size_t n, size_t cap, const ChainPlanes &pl,
-                               uint16_t *cls_cur, uint16_t *cls_other, const SlabGeom &g, const uint64_t *pairs,
-                               size_t npairs, cudaStream_t st)
-{
-    if (n == 0 || npairs == 0) return cudaSuccess;
-    size_t nbp = (npairs + 255) / 256;
-    if (nbp > 148 * 16) nbp = 148 * 16;
-    size_t nbe = (n + 255) / 256;
-    if (nbe > 148 * 16) nbe = 148 * 16;
-    chain_mark_kernel<<<(unsigned)nbp, 256, 0, st>>>(cls_cur, g, pairs, npairs);
-    chain_evict_kernel<<<(unsigned)nbe, 256, 0, st>>>(idx, state, n, cap, pl, cls_cur);
-    chain_unmark_kernel<<<(unsigned)nbp, 256, 0, st>>>(cls_cur, cls_other, g, pairs, npairs);
+    if (t.n == 0 || npairs == 0) return cudaSuccess;
+    size_t nb = (npairs + 7) / 8;  // 8 warps per block
+    if (nb > 148 * 16) nb = 148 * 16;
+    chain_evict_kernel<<<(unsigned)nb, 256, 0, st>>>(t, pl, cls_cur, cls_other, g, pairs, npairs, parity & 1u);
     return cudaGetLastError();
 }
 
@@ -625,33 +725,30 @@ __device__ __forceinline__ bool same_bits17(const float (&a)[8], const float (&b
     return same;
 }
 
-// Advance every chain by nsteps collides: step s collides the copy in buffer (parity0 + s) % 2.
-// Exact shortcut: once a pair of steps leaves all 17 floats bit-identical, every later pair does too
-// (same deterministic map, same omega), so the remaining pairs are skipped.
-__global__ void __launch_bounds__(128) chain_replay_kernel(const uint32_t *idx, float *state, size_t n, size_t cap,
-                                                           uint32_t nsteps, uint32_t parity0, float omega,
-                                                           float *mx, float *my, float *rho)
+// Advance every live, unsettled chain by nsteps collides: step s collides the copy in buffer (parity0 + s) % 2.
+// Exact shortcut: once a pair of steps leaves all 17 floats bit-identical, every later pair does too (same
+// deterministic map, same omega) — the entry is marked settled with both rest values and both moment triples in
+// the table and is skipped from then on.  unsettle: omega changed since the last replay, recompute everything.
+__global__ void __launch_bounds__(128) chain_replay_kernel(const ChainTable t, uint32_t nsteps, uint32_t parity0,
+                                                           float omega, bool unsettle)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || nsteps == 0) return;
-    if (idx[e] == CHAIN_DEAD) return;  // evicted by a paint
-    float a[8], b[8], R;
+    if (e >= t.n || nsteps == 0) return;
+    const uint8_t fl = t.flag[e];
+    if (fl & CHAIN_F_DEAD) return;  // evicted by a paint
+    if ((fl & CHAIN_F_SETTLED) && !unsettle) return;
+    const size_t cap = t.cap;
+    float a[8], b[8];
 #pragma unroll
     for (int d = 0; d < 8; d++) {
-        a[d] = state[(size_t)d * cap + e];
-        b[d] = state[(size_t)(8 + d) * cap + e];
+        a[d] = t.state[(size_t)d * cap + e];
+        b[d] = t.state[(size_t)(8 + d) * cap + e];
     }
-    R = state[(size_t)16 * cap + e];
-    float ai[8], bi[8];  // as loaded: a chain that ends the call where it started is not written back
-#pragma unroll
-    for (int d = 0; d < 8; d++) {
-        ai[d] = a[d];
-        bi[d] = b[d];
-    }
-    const float Ri = R;
-    float m_x = 0.f, m_y = 0.f, r = 0.f;
+    uint32_t par = parity0 & 1u;  // buffer the next collide acts on
+    float R = t.state[(size_t)(CHAIN_ROW_REST + par) * cap + e];
+    float ma[3] = {0.f, 0.f, 0.f}, mb[3] = {0.f, 0.f, 0.f};
+    bool did_a = false, did_b = false, changed = false;
     uint32_t left = nsteps;
-    uint32_t par = parity0 & 1u;
     while (left >= 2) {
         float a0[8], b0[8];
         const float R0 = R;
@@ -660,41 +757,98 @@ __global__ void __launch_bounds__(128) chain_replay_kernel(const uint32_t *idx, 
             a0[d] = a[d];
             b0[d] = b[d];
         }
+        float Rmid;
         if (par == 0) {
-            collide_cell(a, R, omega, m_x, m_y, r);
-            collide_cell(b, R, omega, m_x, m_y, r);
+            collide_cell(a, R, omega, ma[0], ma[1], ma[2]);
+            Rmid = R;
+            collide_cell(b, R, omega, mb[0], mb[1], mb[2]);
         } else {
-            collide_cell(b, R, omega, m_x, m_y, r);
-            collide_cell(a, R, omega, m_x, m_y, r);
+            collide_cell(b, R, omega, mb[0], mb[1], mb[2]);
+            Rmid = R;
+            collide_cell(a, R, omega, ma[0], ma[1], ma[2]);
         }
         left -= 2;
-        if (same_bits17(a, b, R, a0, b0, R0)) left &= 1u;  // fixed point of the two-step map
+        if (same_bits17(a, b, R, a0, b0, R0)) {
+            // exact period-2 cycle: rest is R before a collide of buffer `par`, Rmid before one of the other
+            if (changed) {
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    t.state[(size_t)d * cap + e] = a[d];
+                    t.state[(size_t)(8 + d) * cap + e] = b[d];
+                }
+            }
+            t.state[(size_t)(CHAIN_ROW_REST + par) * cap + e] = R;
+            t.state[(size_t)(CHAIN_ROW_REST + (par ^ 1u)) * cap + e] = Rmid;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                t.state[(size_t)(CHAIN_ROW_MOM + q) * cap + e] = ma[q];
+                t.state[(size_t)(CHAIN_ROW_MOM + 3 + q) * cap + e] = mb[q];
+            }
+            t.flag[e] = CHAIN_F_SETTLED;
+            return;
+        }
+        changed = true;
+        did_a = did_b = true;
     }
     if (left) {
-        if (par == 0) collide_cell(a, R, omega, m_x, m_y, r);
-        else collide_cell(b, R, omega, m_x, m_y, r);
-    }
-    if (!same_bits17(a, b, R, ai, bi, Ri)) {
-#pragma unroll
-        for (int d = 0; d < 8; d++) {
-            state[(size_t)d * cap + e] = a[d];
-            state[(size_t)(8 + d) * cap + e] = b[d];
+        if (par == 0) {
+            collide_cell(a, R, omega, ma[0], ma[1], ma[2]);
+            did_a = true;
+        } else {
+            collide_cell(b, R, omega, mb[0], mb[1], mb[2]);
+            did_b = true;
         }
-        state[(size_t)16 * cap + e] = R;
+        par ^= 1u;
     }
-    const size_t i = idx[e];
-    mx[i] = m_x;
-    my[i] = m_y;
-    rho[i] = r;
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+        t.state[(size_t)d * cap + e] = a[d];
+        t.state[(size_t)(8 + d) * cap + e] = b[d];
+    }
+    t.state[(size_t)(CHAIN_ROW_REST + par) * cap + e] = R;
+    if (did_a) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) t.state[(size_t)(CHAIN_ROW_MOM + q) * cap + e] = ma[q];
+    }
+    if (did_b) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) t.state[(size_t)(CHAIN_ROW_MOM + 3 + q) * cap + e] = mb[q];
+    }
+    if (fl & CHAIN_F_SETTLED) t.flag[e] = 0;
 }
 
-cudaError_t launch_chain_replay(const uint32_t *idx, float *state, size_t n, size_t cap, uint32_t nsteps,
-                                uint32_t parity0, float omega, float *mx, float *my, float *rho, cudaStream_t st)
+cudaError_t launch_chain_replay(const ChainTable &t, uint32_t nsteps, uint32_t parity0, float omega, bool unsettle,
+                                cudaStream_t st)
 {
-    if (n == 0 || nsteps == 0) return cudaSuccess;
-    const size_t nb = (n + 127) / 128;
+    if (t.n == 0 || nsteps == 0) return cudaSuccess;
+    const size_t nb = (t.n + 127) / 128;
     if (nb > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    chain_replay_kernel<<<(unsigned)nb, 128, 0, st>>>(idx, state, n, cap, nsteps, parity0, omega, mx, my, rho);
+    chain_replay_kernel<<<(unsigned)nb, 128, 0, st>>>(t, nsteps, parity0, omega, unsettle);
+    return cudaGetLastError();
+}
+
+// moments of the latest collide of buffer `last_parity`, table -> planes (scattered 4-byte stores: only the
+// scalar kernel's moment-storing launches need the planes to hold them beforehand)
+__global__ void chain_scatter_moments_kernel(const ChainTable t, const uint32_t last_parity, float *mx, float *my,
+                                             float *rho)
+{
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < t.n; e += (size_t)gridDim.x * blockDim.x) {
+        if (t.flag[e] & CHAIN_F_DEAD) continue;
+        const size_t i = t.idx[e];
+        const float *m = t.state + (size_t)(CHAIN_ROW_MOM + 3 * last_parity) * t.cap + e;
+        mx[i] = m[0];
+        my[i] = m[t.cap];
+        rho[i] = m[2 * t.cap];
+    }
+}
+
+cudaError_t launch_chain_scatter_moments(const ChainTable &t, uint32_t last_parity, float *mx, float *my, float *rho,
+                                         cudaStream_t st)
+{
+    if (t.n == 0) return cudaSuccess;
+    size_t nb = (t.n + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    chain_scatter_moments_kernel<<<(unsigned)nb, 256, 0, st>>>(t, last_parity & 1u, mx, my, rho);
     return cudaGetLastError();
 }
 
@@ -796,12 +950,14 @@ cudaError_t preload_aux_kernels()
     BLBM_TOUCH(wait_kernel);
     BLBM_TOUCH(chain_count_kernel);
     BLBM_TOUCH(mailbox_kernel);
-    BLBM_TOUCH(chain_build_kernel);
+    BLBM_TOUCH(scan_tiles_kernel);
+    BLBM_TOUCH(scan_sums_kernel);
+    BLBM_TOUCH(scan_add_kernel);
+    BLBM_TOUCH(chain_fill_kernel);
     BLBM_TOUCH(chain_flush_kernel);
-    BLBM_TOUCH(chain_mark_kernel);
     BLBM_TOUCH(chain_evict_kernel);
-    BLBM_TOUCH(chain_unmark_kernel);
     BLBM_TOUCH(chain_replay_kernel);
+    BLBM_TOUCH(chain_scatter_moments_kernel);
     BLBM_TOUCH(color_map_kernel);
     return cudaSuccess;
 }

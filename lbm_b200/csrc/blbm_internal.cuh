@@ -26,13 +26,21 @@ __host__ __device__ constexpr int dir_opp(int d) { return 7 - d; }
 //   bit 8      skipped by stream (barrier | x == 0 | y >= H-1)
 //   bit 9      state lives in the barrier-chain table; plane slots are don't-care
 //   bit 10     barrier
-//   bit 11     scratch mark while a paint evicts cells from the chain table
+//   bit 12     the cell owns a slot of the barrier-chain table (live: bit 9 set too; evicted by a paint: bit 9
+//              clear).  The table is ordered by plane offset, so the slot of a cell is the number of slot bits in
+//              front of it: a per-chunk base (one u32 per 128 cells) plus a prefix count inside the chunk.
 constexpr uint16_t CLS_UP_MASK = 0xffu;
 constexpr uint16_t CLS_SKIP = 1u << 8;
 constexpr uint16_t CLS_CHAIN = 1u << 9;
 constexpr uint16_t CLS_BARRIER = 1u << 10;
-constexpr uint16_t CLS_DIRTY = 1u << 11;
-constexpr uint32_t CHAIN_DEAD = 0xffffffffu;
+constexpr uint16_t CLS_SLOT = 1u << 12;
+// per-entry flag byte of the chain table
+constexpr uint8_t CHAIN_F_DEAD = 1u;     // evicted by a paint: the slot stays (ranks must not shift), the state is gone
+constexpr uint8_t CHAIN_F_SETTLED = 2u;  // bitwise period-2 cycle reached: nothing left to compute until omega changes
+// rows of the chain table (each `cap` floats long): 0..7 buffer-0 populations (Dir order), 8..15 buffer-1,
+// 16/17 the rest population as it stands before a collide of the buffer-0 / buffer-1 copy,
+// 18..20 / 21..23 (mx, my, rho) of the latest collide of the buffer-0 / buffer-1 copy
+constexpr int CHAIN_ROW_REST = 16, CHAIN_ROW_MOM = 18, CHAIN_ROWS = 24;
 __host__ __device__ constexpr uint16_t cls_upstream_bit(int d) { return (uint16_t)(1u << d); }
 // public word (blbm.h)
 constexpr uint16_t PUB_BARRIER = 1u, PUB_SKIP = 2u;
@@ -68,6 +76,11 @@ struct StepParams {
     uint64_t Hg;      // global lattice height
     float omega;
     PushTargets push;
+    // barrier-chain table, needed by a moment-storing launch only: slot base per (row, 128-cell chunk) and the
+    // (mx, my, rho) rows (each chain_cap long) of the collide that the launch's moments belong to
+    const uint32_t *chunk_base;
+    const float *chain_mom;
+    uint32_t chain_cap;
 };
 
 // device row index of owned row r in [0, rows): one halo/guard row above
@@ -255,6 +268,25 @@ __device__ __forceinline__ void precollision_moments(const float (&f)[8], float 
 
 enum StepMode { MODE_FUSED = 0, MODE_COLLIDE_ONLY = 1, MODE_STREAM_ONLY = 2 };
 
+// exclusive prefix sum over the lanes of a (fully converged) warp; *total = sum over the warp
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, uint32_t *total)
+{
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (total) *total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+// how many of four class words have `bit` set
+__device__ __forceinline__ uint32_t count4(const ushort4 c, const uint16_t bit)
+{
+    return ((c.x & bit) ? 1u : 0u) + ((c.y & bit) ? 1u : 0u) + ((c.z & bit) ? 1u : 0u) + ((c.w & bit) ? 1u : 0u);
+}
+
 // force the lazy module load of every kernel of the library (see aux_kernels.cu)
 cudaError_t preload_aux_kernels();
 cudaError_t preload_step_kernels();
@@ -301,19 +333,31 @@ cudaError_t launch_reduce(const float *mx, const float *my, const float *rho, co
 struct ChainPlanes {
     float *f0[8], *f1[8], *R;
 };
-cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, unsigned long long *count,
+struct ChainTable {
+    uint32_t *idx;         // plane offset of every slot, ascending
+    uint8_t *flag;         // CHAIN_F_*
+    float *state;          // CHAIN_ROWS x cap
+    uint32_t *chunk_base;  // slots in front of each (row, chunk), row-major over the owned rows
+    size_t n, cap;
+};
+// counts the barrier cells of every (row, chunk) into chunk_cnt and their total into *count, then posts the
+// total to a mapped host word
+cudaError_t launch_chain_count(const uint16_t *cls, const SlabGeom &g, uint32_t *chunk_cnt, unsigned long long *count,
                                unsigned long long *host_mailbox, cudaStream_t st);
+// chunk_cnt -> exclusive prefix in place (scratch: one u32 per 1024 chunks), then planes -> table in plane order
 cudaError_t launch_chain_build(uint16_t *cls, uint16_t *cls_other, const SlabGeom &g, const ChainPlanes &pl,
-                               uint32_t *idx, float *state, size_t cap, unsigned long long *cursor, cudaStream_t st);
-cudaError_t launch_chain_flush(const uint32_t *idx, const float *state, size_t n, size_t cap,
-                               const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1, cudaStream_t st);
+                               const ChainTable &t, uint32_t *scan_scratch, uint32_t parity, cudaStream_t st);
+cudaError_t launch_chain_flush(const ChainTable &t, const ChainPlanes &pl, uint16_t *cls0, uint16_t *cls1,
+                               uint32_t parity, cudaStream_t st);
 // a paint is about to change the mask at `pairs` (global location, value): move those cells' chains back
-// into the planes and drop them from the table
-cudaError_t launch_chain_evict(uint32_t *idx, const float *state, size_t n, size_t cap, const ChainPlanes &pl,
-                               uint16_t *cls_cur, uint16_t *cls_other, const SlabGeom &g, const uint64_t *pairs,
-                               size_t npairs, cudaStream_t st);
-cudaError_t launch_chain_replay(const uint32_t *idx, float *state, size_t n, size_t cap, uint32_t nsteps,
-                                uint32_t parity0, float omega, float *mx, float *my, float *rho, cudaStream_t st);
+// into the planes and mark their slots dead
+cudaError_t launch_chain_evict(const ChainTable &t, const ChainPlanes &pl, uint16_t *cls_cur, uint16_t *cls_other,
+                               const SlabGeom &g, const uint64_t *pairs, size_t npairs, uint32_t parity, cudaStream_t st);
+cudaError_t launch_chain_replay(const ChainTable &t, uint32_t nsteps, uint32_t parity0, float omega, bool unsettle,
+                                cudaStream_t st);
+// table moments -> moment planes (only in front of a moment-storing launch of the scalar kernel)
+cudaError_t launch_chain_scatter_moments(const ChainTable &t, uint32_t last_parity, float *mx, float *my, float *rho,
+                                         cudaStream_t st);
 
 cudaError_t launch_signal(unsigned long long *remote_up, unsigned long long *remote_dn,
                           unsigned long long epoch, cudaStream_t st);

@@ -111,8 +111,12 @@ struct blbm_handle {
     bool chain_active = false;   // barrier slots of the planes are don't-care, their state is in the table
     bool chain_declined = false; // auto mode looked at the current mask and decided against
     uint32_t *chain_idx = nullptr;
+    uint8_t *chain_flag = nullptr;
     float *chain_state = nullptr;
     size_t chain_n = 0, chain_cap = 0;
+    uint32_t *chunk_base = nullptr;    // slots in front of each (row, 128-cell chunk); per-chunk counts while building
+    uint32_t *scan_scratch = nullptr;  // one word per 1024 chunks
+    bool chain_unsettle = false;       // omega changed: settled chains must be recomputed by the next replay
     unsigned long long *chain_counter = nullptr;
     unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
     // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): GRAPH_CHUNK fused steps are

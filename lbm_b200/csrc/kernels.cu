@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) step_scalar_kernel(const StepParams p)
 #pragma unroll
     for (int d = 0; d < 8; d++) p.Y[d][i] = f[d];
     if (MOM) {
-        if (lazy_barrier) {  // the chain kernel already stored this cell's moments
+        if (lazy_barrier) {  // the planes already hold this cell's moments (chain_scatter_moments_kernel)
             mx = p.mx[i];
             my = p.my[i];
         } else {
@@ -235,8 +235,16 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32
             rsw = ssw_;
         }
     }
+    if (LATE_CLS && valid && flag != 0) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
+    // moment-storing launch with the barrier-chain table active: the table slot of this lane's first slot-owning
+    // cell = chunk base + slot bits in front of it (the table is ordered by plane offset); the whole warp takes part
+    uint32_t slot_e = 0;
+    if (MOM && p.chain_mom != nullptr) {
+        uint32_t total;
+        const uint32_t before = warp_excl_scan(count4(c4, CLS_SLOT), lane, &total);
+        if (total) slot_e = p.chunk_base[(size_t)r * nbx + bx] + before;
+    }
     if (!valid) return;  // (lanes past the row end issued no cp.async)
-    if (LATE_CLS && flag != 0) c4 = *reinterpret_cast<const ushort4 *>(p.cls + i);
 
     g[0][D_N] = vn.x; g[1][D_N] = vn.y; g[2][D_N] = vn.z; g[3][D_N] = vn.w;
     g[0][D_S] = vs.x; g[1][D_S] = vs.y; g[2][D_S] = vs.z; g[3][D_S] = vs.w;
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32
             }
         }
     }
-    finish_group<MOM, PACKED, IDX>(p, i, x4, r, g, c0, c1, c2, c3, vr);
+    finish_group<MOM, PACKED, IDX>(p, i, x4, r, g, c0, c1, c2, c3, vr, slot_e);
     if (STAGED) cp_async_wait_all();  // nothing may still be landing in shared memory when the block retires
 }
 

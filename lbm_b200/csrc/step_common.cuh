@@ -38,7 +38,8 @@ __device__ __forceinline__ bool reloads_own(const uint32_t c)
 template <bool MOM, bool PACKED = false, typename IDX = size_t>
 __device__ __forceinline__ void finish_group(const StepParams &p, const IDX i, const uint32_t x4, const uint32_t r,
                                              float (&g)[4][8], const uint32_t c0, const uint32_t c1,
-                                             const uint32_t c2, const uint32_t c3, const float4 vr)
+                                             const uint32_t c2, const uint32_t c3, const float4 vr,
+                                             const uint32_t slot_e)
 {
     const uint32_t P = p.P, W = p.W;
     const uint32_t cany = c0 | c1 | c2 | c3;
@@ -91,12 +92,19 @@ __device__ __forceinline__ void finish_group(const StepParams &p, const IDX i, c
     for (int d = 0; d < 8; d++) stg4(p.Y[d] + i, make_float4(g[0][d], g[1][d], g[2][d], g[3][d]));
     if (MOM) {
         if (cany & CLS_CHAIN) {
-            // keep the moments the barrier-chain kernel stored at chain cells
-            const float4 ex = ldg4(p.mx + i), ey = ldg4(p.my + i), er = ldg4(p.rho + i);
-            if (c0 & CLS_CHAIN) { mx[0] = ex.x; my[0] = ey.x; rho[0] = er.x; }
-            if (c1 & CLS_CHAIN) { mx[1] = ex.y; my[1] = ey.y; rho[1] = er.y; }
-            if (c2 & CLS_CHAIN) { mx[2] = ex.z; my[2] = ey.z; rho[2] = er.z; }
-            if (c3 & CLS_CHAIN) { mx[3] = ex.w; my[3] = ey.w; rho[3] = er.w; }
+            // chain cells: their plane slots are don't-care, the moments of their latest collide are in the table,
+            // slot_e onwards in plane order (dead slots still count)
+            const uint32_t cq[4] = {c0, c1, c2, c3};
+            uint32_t e = slot_e;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (cq[q] & CLS_CHAIN) {
+                    mx[q] = p.chain_mom[e];
+                    my[q] = p.chain_mom[(size_t)p.chain_cap + e];
+                    rho[q] = p.chain_mom[2 * (size_t)p.chain_cap + e];
+                }
+                if (cq[q] & CLS_SLOT) e++;
+            }
         }
         stg4(p.mx + i, make_float4(mx[0], mx[1], mx[2], mx[3]));
         stg4(p.my + i, make_float4(my[0], my[1], my[2], my[3]));

@@ -648,3 +648,54 @@ def test_paint_frames_never_synchronise_and_stay_exact():
     assert_same_bits(outs[1].numpy(), ora.output(), "async output of the last frame")
     compare_state(lbm, ora, "after 12 pipelined paint frames")
     lbm.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("omega", [1.0, 1.0 / (3 * 0.02 + 0.5)])
+def test_chain_table_settles_unsettles_and_evicts_exactly(kernel, omega):
+    """The ordered barrier-chain table through its whole life on a 15 % porous lattice: chains settle on their exact
+    period-2 cycle (both rest values and both moment triples in the table), calls of odd and even length and single
+    steps pick the right phase, a paint evicts settled and unsettled entries by slot rank (dead slots keep the
+    ranks of their successors), an omega change unsettles everything, and a flush returns every barrier cell to the
+    planes — bit for bit against the oracle at every stage."""
+    w, h = 300, 70
+    lbm, ora = LBM(omega, w, h, inflow_ux=0.05, kernel=kernel, lazy_barriers=1), Oracle(omega, w, h, inflow_ux=0.05)
+    pts = porous_pairs(w, h)
+    lbm.draw_points(pts)
+    ora.draw_points(pts.astype(np.uint32))
+    rng = np.random.default_rng(11)
+    stage = 0
+
+    def both(n):
+        nonlocal stage
+        lbm.iterate(n); ora.iterate(n)
+        stage += 1
+        assert lbm.lazy_barriers_active()
+        compare_state(lbm, ora, f"chain life stage {stage} (+{n} steps)", populations=(stage % 3 == 0))
+
+    for n in (1, 1, 2, 15, 40, 1, 15, 15, 2):
+        both(n)
+    # evict a mix of barrier cells (settled by now for omega = 1) and paint new ones, mid-table and at chunk edges
+    bar = np.flatnonzero(ora.barrier().reshape(-1) == 1)
+    gone = rng.choice(bar[(bar > w) & (bar < w * (h - 1))], size=200, replace=False)
+    new = rng.integers(w + 2, w * (h - 1) - 2, size=150)
+    pairs = np.concatenate([np.stack([gone, np.zeros_like(gone)], 1), np.stack([new, np.ones_like(new)], 1)])
+    lbm.draw_points(pairs.astype(np.uint32)); ora.draw_points(pairs.astype(np.uint32))
+    for n in (1, 14, 3):
+        both(n)
+    lbm.update_omega_buffer(1.37); ora.update_omega_buffer(1.37)
+    for n in (1, 2, 31):
+        both(n)
+    # re-barrier some of the evicted cells (dead slots stay dead; the cells run densely), evict more
+    back = gone[:60]
+    more = rng.choice(bar[(bar > w) & (bar < w * (h - 1))], size=120, replace=False)
+    pairs = np.concatenate([np.stack([back, np.ones_like(back)], 1), np.stack([more, np.zeros_like(more)], 1)])
+    lbm.draw_points(pairs.astype(np.uint32)); ora.draw_points(pairs.astype(np.uint32))
+    for n in (5, 1, 16):
+        both(n)
+    lbm.collide(); ora.collide()  # leaves the table: everything back in the planes
+    assert not lbm.lazy_barriers_active()
+    compare_state(lbm, ora, "chain life after flush")
+    lbm.iterate(7); ora.iterate(7)  # and re-enters it
+    compare_state(lbm, ora, "chain life after re-entry")
+    lbm.close()
