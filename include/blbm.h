@@ -253,7 +253,10 @@ typedef enum blbm_tune {
     BLBM_TUNE_CUDA_GRAPHS = 5,     /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
     BLBM_TUNE_VEC4_PACKED = 6,     /* collide cell pairs with packed fp32 adds (sm_100 FADD2): 0 (default) or 1; same bits,
                                       measured slower (register pressure) */
-    BLBM_TUNE_VEC4_INDEX32 = 7     /* 32-bit plane offsets where a plane has < 2^32 elements: -1 auto (default, = 1), 0, 1 */
+    BLBM_TUNE_VEC4_INDEX32 = 7,    /* 32-bit plane offsets where a plane has < 2^32 elements: -1 auto (default, = 1), 0, 1 */
+    BLBM_TUNE_LINK_IN_KERNEL = 8   /* linked slabs: 1 (default) the fused step kernel waits for / publishes the halo
+                                      epochs itself (face row blocks first, interior rows overlap the exchange);
+                                      0 one-thread wait and signal kernels around every launch */
 } blbm_tune;
 int blbm_set_tuning(blbm_t *h, int knob, int value);
 /* Barrier cells are isolated (nothing reads them; the reference merely keeps colliding their stale

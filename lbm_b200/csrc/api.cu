@@ -235,10 +235,28 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     if (pushes) p.push = push_targets(h, ybuf);
     int rc;
     if (h->halo_dirty && any_peer(h) && mode != MODE_COLLIDE_ONLY && (rc = push_all_halos(h)) != BLBM_OK) return rc;
-    rc = sync_peers(h);
-    if (rc) return rc;
     int k = h->kernel;
     if (mode != MODE_FUSED) k = BLBM_KERNEL_SCALAR;
+    // Linked slabs: the fused vec4 kernel does the epoch handshake itself (its face row blocks wait, store, and the
+    // last of them publishes the new epoch); every other launch is bracketed by the one-thread wait / signal kernels.
+    const bool link_in_kernel = any_peer(h) && k == BLBM_KERNEL_VEC4 && h->link_in_kernel &&
+                                vec4_links_in_kernel(h->vec4_rows, h->vec4_packed != 0);
+    if (link_in_kernel) {
+        p.link.wait_up = h->up.linked ? h->flags : nullptr;
+        p.link.wait_dn = h->dn.linked ? h->flags + 16 : nullptr;
+        // our word in the slab above is its "from below" flag, and vice versa
+        p.link.sig_up =
+            h->up.linked ? reinterpret_cast<unsigned long long *>(h->up.base + h->up.info.off_flags) + 16 : nullptr;
+        p.link.sig_dn = h->dn.linked ? reinterpret_cast<unsigned long long *>(h->dn.base + h->dn.info.off_flags) : nullptr;
+        p.link.wait_epoch = h->epoch;
+        p.link.sig_epoch = h->epoch + 1;
+        p.link.done = h->link_done;
+        p.link.err_flag = h->err_flag;
+        p.link.timeout_ns = h->wait_timeout_ns;
+    } else {
+        rc = sync_peers(h);
+        if (rc) return rc;
+    }
     cudaError_t e;
     if (mom && h->chain_active) {
         // chain cells' moments (of the collide of buffer `ybuf`, which this launch performs for every other cell)
@@ -269,6 +287,11 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
     if (e != cudaSuccess) return fail(BLBM_ECUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
     h->launches++;
     if (mode == MODE_COLLIDE_ONLY) h->halo_dirty = false;  // this launch pushed the live buffer's boundary rows
+    if (link_in_kernel) {
+        h->waited = h->epoch;
+        h->epoch++;
+        return BLBM_OK;
+    }
     if (pushes) return signal_peers(h);
     return BLBM_OK;
 }
@@ -744,7 +767,7 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     const size_t off_ss = carve((flag_bytes / 1024 + 1) * sizeof(uint32_t));
     const size_t off_mask = carve((size_t)(h->rows + 4) * h->P);
     h->off_flags = carve(256);
-    const size_t off_err = carve(64), off_red = carve(64), off_cnt = carve(64);
+    const size_t off_err = carve(64), off_red = carve(64), off_cnt = carve(64), off_done = carve(64);
     h->pool_bytes = off;
     e = cudaMalloc(&h->pool, h->pool_bytes);
     if (e != cudaSuccess) {
@@ -770,6 +793,7 @@ int blbm_create_slab(uint32_t w, uint64_t h_global, uint64_t row_begin, uint64_t
     h->red_sums = reinterpret_cast<double *>(h->pool + off_red);
     h->red_max = reinterpret_cast<float *>(h->pool + off_red + 32);
     h->chain_counter = reinterpret_cast<unsigned long long *>(h->pool + off_cnt);
+    h->link_done = reinterpret_cast<unsigned int *>(h->pool + off_done);
 
     int rc = BLBM_OK;
     do {
@@ -1441,6 +1465,10 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
     case BLBM_TUNE_VEC4_INDEX32:
         if (value < -1 || value > 1) return fail(BLBM_EINVAL, "index32 must be -1 (auto), 0 or 1");
         h->vec4_index32 = value;
+        return BLBM_OK;
+    case BLBM_TUNE_LINK_IN_KERNEL:
+        if (value != 0 && value != 1) return fail(BLBM_EINVAL, "in-kernel handshake must be 0 or 1");
+        h->link_in_kernel = value;
         return BLBM_OK;
     case BLBM_TUNE_CUDA_GRAPHS:
         if (value < -1 || value > 1) return fail(BLBM_EINVAL, "graphs must be -1 (auto), 0 or 1");

@@ -61,6 +61,20 @@ struct PushTargets {
     float *up_mx, *up_my, *dn_mx, *dn_my;
 };
 
+// Epoch handshake with the neighbouring slabs, executed INSIDE the fused vec4 step kernel (sig_epoch != 0): only the
+// row blocks at a slab face read halo rows or store into a neighbour's; they wait (one thread spins on our flag word
+// with ld.acquire.sys) until that neighbour has published wait_epoch, and after their last store they arrive on a
+// per-face counter whose last arrival publishes sig_epoch to the neighbour with st.release.sys.  Those row blocks
+// are scheduled first, so the flags go out at the start of a launch and interior rows overlap the exchange.
+struct LinkSync {
+    const unsigned long long *wait_up, *wait_dn;  // our flag words, written by the slab above / below (null: none)
+    unsigned long long *sig_up, *sig_dn;          // the neighbours' flag words for us
+    unsigned long long wait_epoch, sig_epoch;
+    unsigned int *done;  // [0] arrivals of the up-face blocks of this launch, [1] of the down-face blocks
+    int *err_flag;
+    unsigned long long timeout_ns;
+};
+
 struct StepParams {
     const float *X[8];  // source buffer: post-collision populations T_{k-1} (rows incl. halos)
     float *Y[8];        // destination buffer
@@ -81,6 +95,7 @@ struct StepParams {
     const uint32_t *chunk_base;
     const float *chain_mom;
     uint32_t chain_cap;
+    LinkSync link;
 };
 
 // device row index of owned row r in [0, rows): one halo/guard row above
@@ -295,8 +310,11 @@ cudaError_t preload_step_kernels();
 cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments, cudaStream_t st);
 // dense_obstacles: 0 sparse fix-up (one branch per direction), 1 branch-free, 2 branch-free + cp.async staging
 // index32: use 32-bit plane offsets where the slab allows it
+// p.link.sig_epoch != 0 selects the variant with the in-kernel neighbour handshake (fused mode only; needs
+// vec4_links_in_kernel(block_rows, packed))
 cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, int dense_obstacles,
                              bool packed, bool index32, cudaStream_t st);
+bool vec4_links_in_kernel(int block_rows, bool packed);
 
 // ---- auxiliary kernels (aux_kernels.cu) ----------------------------------------------------------
 // Slab geometry shared by the auxiliary launchers.  Population/moment/class planes have rows+3 device

@@ -95,6 +95,8 @@ struct blbm_handle {
     uint64_t launches = 0;
     blbmh::Peer up, dn;
     unsigned long long epoch = 0, waited = 0;
+    unsigned int *link_done = nullptr;  // per-face arrival counters of the in-kernel handshake (LinkSync)
+    int link_in_kernel = 1;             // fused vec4 launches of linked slabs wait and signal inside the kernel
     unsigned long long wait_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
     uint64_t *d_pairs = nullptr;
     size_t d_pairs_cap = 0;

@@ -145,6 +145,40 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- in-kernel epoch handshake of linked slabs (LinkSync, blbm_internal.cuh) ---------------------------------
+__device__ __forceinline__ void link_wait(const unsigned long long *from_up, const unsigned long long *from_dn,
+                                       const unsigned long long epoch, int *err_flag, const unsigned long long timeout_ns)
+{
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long u = epoch, d = epoch;
+        if (from_up) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(u) : "l"(from_up) : "memory");
+        if (from_dn) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(d) : "l"(from_dn) : "memory");
+        if (u >= epoch && d >= epoch) return;
+        if (*reinterpret_cast<volatile int *>(err_flag)) return;  // an earlier wait already gave up
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {  // never hang the GPU on a dead neighbour: flag and carry on
+            *err_flag = 1;
+            return;
+        }
+        __nanosleep(100);
+    }
+}
+
+// the last of `target` blocks to arrive publishes the epoch to the neighbour and re-arms the counter
+__device__ __forceinline__ void link_arrive(unsigned int *counter, const unsigned int target, unsigned long long *remote_flag,
+                                         const unsigned long long epoch)
+{
+    __threadfence_system();
+    if (atomicAdd(counter, 1u) == target - 1u) {
+        *counter = 0u;  // the next launch on this stream starts after this one has drained
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(epoch) : "memory");
+    }
+}
 // own-row plane of staging slot q (the opposite of the directions that move in y)
 __host__ __device__ constexpr int stage_dir(int q) { return q == 0 ? D_NW : q == 1 ? D_N : q == 2 ? D_NE : q == 3 ? D_SW : q == 4 ? D_S : D_SE; }
 __host__ __device__ constexpr int stage_slot(int d) { return d == D_NW ? 0 : d == D_N ? 1 : d == D_NE ? 2 : d == D_SW ? 3 : d == D_S ? 4 : 5; }
@@ -154,8 +188,10 @@ __host__ __device__ constexpr int stage_slot(int d) { return d == D_NW ? 0 : d =
 // rows-per-block 4), size_t otherwise.  The grid is (chunks along x, row blocks [, overflow of row blocks]) so that
 // no thread divides a linear block index.
 constexpr uint32_t GRID_Y = 32768;
-template <bool MOM, int V4_ROWS, int DENSE, bool PACKED, typename IDX>
-__global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
+// LINKED: the epoch handshake with the neighbouring slabs runs inside the kernel (LinkSync); a separate instantiation
+// so that the unlinked kernel keeps its 64-register budget.
+template <bool MOM, int V4_ROWS, int DENSE, bool PACKED, typename IDX, bool LINKED = false>
+__global__ void __launch_bounds__(32 * V4_ROWS, (DENSE || LINKED) ? (MOM ? 768 : 1024) / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
 {
     constexpr bool STAGED = DENSE >= 2;
     constexpr bool EAGER_CLS = DENSE == 3;  // class words read up front, without the chunk-flag test
@@ -166,7 +202,25 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32
     const uint32_t tid = threadIdx.y * 32u + threadIdx.x;
     const uint32_t nbx = gridDim.x;  // = ceil(P / 128)
     const uint32_t bx = blockIdx.x;
-    const uint32_t r = (blockIdx.z * GRID_Y + blockIdx.y) * V4_ROWS + threadIdx.y;
+    uint32_t rb = blockIdx.z * GRID_Y + blockIdx.y;  // row block
+    bool face_up = false, face_dn = false;
+    if (LINKED) {
+        // linked slab, handshake in-kernel: the row blocks at the two faces come first in launch order ...
+        const uint32_t nrb = (p.rows + V4_ROWS - 1) / V4_ROWS;
+        if (nrb >= 4) rb = rb == 0 ? 0u : rb == 1 ? nrb - 1 : rb == 2 ? nrb - 2 : rb - 2;
+        // ... and are the only ones that touch halo rows: row 0 gathers from the halo above and rows 0-1 store into
+        // the slab above; rows-1 gathers from the halo below (rows-2 too, through the flat-index wrap of column
+        // W-1) and stores into the slab below
+        face_up = p.link.sig_up != nullptr && rb == 0;
+        face_dn = p.link.sig_dn != nullptr && (rb == (p.rows - 1) / V4_ROWS || rb == (p.rows - 2) / V4_ROWS);
+        if (face_up || face_dn) {
+            if (tid == 0)
+                link_wait(face_up ? p.link.wait_up : nullptr, face_dn ? p.link.wait_dn : nullptr, p.link.wait_epoch,
+                          p.link.err_flag, p.link.timeout_ns);
+            __syncthreads();  // every warp of the block is still here
+        }
+    }
+    const uint32_t r = rb * V4_ROWS + threadIdx.y;
     if (r >= p.rows) return;  // whole warps leave together (a warp is one row)
     const uint32_t lane = threadIdx.x;
     const uint32_t x4 = bx * 128u + lane * 4u;
@@ -244,8 +298,7 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32
         const uint32_t before = warp_excl_scan(count4(c4, CLS_SLOT), lane, &total);
         if (total) slot_e = p.chunk_base[(size_t)r * nbx + bx] + before;
     }
-    if (!valid) return;  // (lanes past the row end issued no cp.async)
-
+    if (valid) {  // (lanes past the row end issued no cp.async and have nothing to store)
     g[0][D_N] = vn.x; g[1][D_N] = vn.y; g[2][D_N] = vn.z; g[3][D_N] = vn.w;
     g[0][D_S] = vs.x; g[1][D_S] = vs.y; g[2][D_S] = vs.z; g[3][D_S] = vs.w;
     g[0][D_E] = le; g[1][D_E] = ve.x; g[2][D_E] = ve.y; g[3][D_E] = ve.z;
@@ -305,9 +358,27 @@ __global__ void __launch_bounds__(32 * V4_ROWS, DENSE ? (MOM ? 768 : 1024) / (32
     }
     finish_group<MOM, PACKED, IDX>(p, i, x4, r, g, c0, c1, c2, c3, vr, slot_e);
     if (STAGED) cp_async_wait_all();  // nothing may still be landing in shared memory when the block retires
+    }
+    if (LINKED && (face_up || face_dn)) {
+        // every thread orders its own stores into the neighbour before the block arrives; the barrier counts the
+        // live warps only (rows past the slab end have left)
+        __threadfence_system();
+        const uint32_t live = (p.rows - rb * V4_ROWS < (uint32_t)V4_ROWS ? p.rows - rb * V4_ROWS : (uint32_t)V4_ROWS) * 32u;
+        asm volatile("bar.sync 1, %0;" ::"r"(live) : "memory");
+        if (tid == 0) {
+            const uint32_t ndn = (p.rows - 1) / V4_ROWS != (p.rows - 2) / V4_ROWS ? 2u : 1u;
+            if (face_up) link_arrive(&p.link.done[0], nbx, p.link.sig_up, p.link.sig_epoch);
+            if (face_dn) link_arrive(&p.link.done[1], nbx * ndn, p.link.sig_dn, p.link.sig_epoch);
+        }
+    }
 }
 
-template <int V4_ROWS, int DENSE, bool PACKED, typename IDX>
+// every element offset a launch forms (rows+3 device rows, one float4 past the last) fits 32 bits
+static bool plane_fits_u32(const StepParams &p) { return ((uint64_t)p.rows + 3u) * p.P + 8u < (1ull << 32); }
+
+bool vec4_links_in_kernel(int block_rows, bool packed) { return block_rows == 4 && !packed; }
+
+template <int V4_ROWS, int DENSE, bool PACKED, typename IDX, bool LINKED = false>
 static cudaError_t launch_vec4_idx(const StepParams &p, bool mom, cudaStream_t st)
 {
     const uint32_t nbx = (p.P + 127u) / 128u;
@@ -315,13 +386,11 @@ static cudaError_t launch_vec4_idx(const StepParams &p, bool mom, cudaStream_t s
     if (nbx == 0 || nrb == 0) return cudaErrorInvalidConfiguration;
     dim3 grid(nbx, nrb < GRID_Y ? nrb : GRID_Y, (nrb + GRID_Y - 1) / GRID_Y), block(32, V4_ROWS);
     if (grid.z > 65535u) return cudaErrorInvalidConfiguration;
-    if (mom) step_vec4_kernel<true, V4_ROWS, DENSE, PACKED, IDX><<<grid, block, 0, st>>>(p);
-    else step_vec4_kernel<false, V4_ROWS, DENSE, PACKED, IDX><<<grid, block, 0, st>>>(p);
+    if (mom) step_vec4_kernel<true, V4_ROWS, DENSE, PACKED, IDX, LINKED><<<grid, block, 0, st>>>(p);
+    else step_vec4_kernel<false, V4_ROWS, DENSE, PACKED, IDX, LINKED><<<grid, block, 0, st>>>(p);
     return cudaGetLastError();
 }
 
-// every element offset a launch forms (rows+3 device rows, one float4 past the last) fits 32 bits
-static bool plane_fits_u32(const StepParams &p) { return ((uint64_t)p.rows + 3u) * p.P + 8u < (1ull << 32); }
 
 // The default block shape (4 rows) exists in every flavour; the other shapes (A/B knob) only with scalar adds and
 // 64-bit offsets.
@@ -329,6 +398,12 @@ template <int DENSE>
 static cudaError_t launch_vec4_flavour(const StepParams &p, bool mom, int block_rows, bool packed, bool index32,
                                        cudaStream_t st)
 {
+    if (p.link.sig_epoch != 0) {
+        // in-kernel handshake: default block shape, scalar adds (vec4_links_in_kernel)
+        if (block_rows != 4 || packed) return cudaErrorInvalidConfiguration;
+        if (index32 && plane_fits_u32(p)) return launch_vec4_idx<4, DENSE, false, uint32_t, true>(p, mom, st);
+        return launch_vec4_idx<4, DENSE, false, size_t, true>(p, mom, st);
+    }
     switch (block_rows) {
     case 1: return launch_vec4_idx<1, DENSE, false, size_t>(p, mom, st);
     case 2: return launch_vec4_idx<2, DENSE, false, size_t>(p, mom, st);
@@ -363,11 +438,11 @@ cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, int block_
         if (e__ != cudaSuccess) return e__;                              \
     } while (0)
 
-template <int ROWS, int DENSE, bool PACKED, typename IDX>
+template <int ROWS, int DENSE, bool PACKED, typename IDX, bool LINKED = false>
 static cudaError_t touch_vec4()
 {
-    BLBM_TOUCH(step_vec4_kernel<false, ROWS, DENSE, PACKED, IDX>);
-    BLBM_TOUCH(step_vec4_kernel<true, ROWS, DENSE, PACKED, IDX>);
+    BLBM_TOUCH(step_vec4_kernel<false, ROWS, DENSE, PACKED, IDX, LINKED>);
+    BLBM_TOUCH(step_vec4_kernel<true, ROWS, DENSE, PACKED, IDX, LINKED>);
     return cudaSuccess;
 }
 
@@ -382,6 +457,8 @@ static cudaError_t touch_vec4_flavour()
     if ((e = touch_vec4<4, DENSE, false, size_t>()) != cudaSuccess) return e;
     if ((e = touch_vec4<4, DENSE, true, size_t>()) != cudaSuccess) return e;
     if ((e = touch_vec4<4, DENSE, false, uint32_t>()) != cudaSuccess) return e;
+    if ((e = touch_vec4<4, DENSE, false, uint32_t, true>()) != cudaSuccess) return e;
+    if ((e = touch_vec4<4, DENSE, false, size_t, true>()) != cudaSuccess) return e;
     return touch_vec4<4, DENSE, true, uint32_t>();
 }
 

@@ -699,3 +699,31 @@ def test_chain_table_settles_unsettles_and_evicts_exactly(kernel, omega):
     lbm.iterate(7); ora.iterate(7)  # and re-enters it
     compare_state(lbm, ora, "chain life after re-entry")
     lbm.close()
+
+
+@pytest.mark.parametrize("in_kernel", [0, 1])
+@pytest.mark.parametrize("size", [(300, 41), (129, 9), (1000, 70)])
+def test_halo_handshake_inside_and_outside_the_step_kernel(size, in_kernel):
+    """Linked slabs publish / await the halo epochs either inside the fused vec4 kernel (face row blocks first; the
+    default) or through the one-thread wait / signal kernels around every launch (knob 8 = 0; also what the scalar
+    kernel and non-default block shapes use): same bits, including slabs of 2-3 rows where every row block is a
+    face block and uneven slab heights where the row above the last sits in its own row block."""
+    w, h = size
+    om = omega_from_viscosity(0.02)
+    for nslabs in (2, 3, 4):
+        if h < 2 * nslabs:
+            continue
+        grp = LBM(om, w, h, devices=_group_devices(nslabs), kernel=Kernel.Vec4)
+        grp.set_tuning(8, in_kernel)
+        ora = Oracle(om, w, h)
+        pts = porous_pairs(w, h, frac=0.1, seed=3)
+        grp.draw_points(pts); ora.draw_points(pts.astype(np.uint32))
+        for n in (1, 2, 37, 64):
+            grp.iterate(n); ora.iterate(n)
+        compare_state(grp, ora, f"handshake in_kernel={in_kernel} {w}x{h} x{nslabs}")
+        grp.set_tuning(0, 8)  # a block shape without the in-kernel variant falls back to the launch-level handshake
+        grp.iterate(5); ora.iterate(5)
+        grp.set_tuning(0, 4)
+        grp.iterate(6); ora.iterate(6)
+        compare_state(grp, ora, f"handshake mixed {w}x{h} x{nslabs}")
+        grp.close()
