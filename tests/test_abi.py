@@ -128,14 +128,17 @@ def test_default_step_kernels_keep_their_register_budget_and_wide_accesses():
     counts, _ = ss.sass_counts()
     names = {ss.short(v): k for k, v in ss.demangle(sorted(res)).items()}
     for flavour in (0, 2):
-        k = names[f"step_vec4_kernel<(bool)0, (int)4, (int){flavour}, (bool)0, u32>"]
+        k = names[f"step_vec4_kernel<(bool)0, (int)4, (int){flavour}, (bool)0, u32, (bool)0>"]
         assert int(res[k]["REG"]) <= 64 and int(res[k]["STACK"]) == 0, (flavour, res[k])
+        # linked slabs (handshake inside the kernel): same occupancy; two block-uniform words may live on the stack
+        kl = names[f"step_vec4_kernel<(bool)0, (int)4, (int){flavour}, (bool)0, u32, (bool)1>"]
+        assert int(res[kl]["REG"]) <= 64 and int(res[kl]["STACK"]) <= 8, (flavour, res[kl])
         c = counts[k]
         assert c["LDG.E.128"] >= 9 and c["STG.E.128"] >= 9 and c["SHFL"] >= 6 and not c["LDL"] and not c["STL"]
         assert (c["LDGSTS"] > 0) == (flavour == 2)
     # the moment-storing launch (one per iterate) may use more registers but must not spill either
     for flavour in (0, 2):
-        k = names[f"step_vec4_kernel<(bool)1, (int)4, (int){flavour}, (bool)0, u32>"]
+        k = names[f"step_vec4_kernel<(bool)1, (int)4, (int){flavour}, (bool)0, u32, (bool)0>"]
         assert int(res[k]["REG"]) <= 80 and int(res[k]["STACK"]) == 0
 
 
