@@ -259,9 +259,9 @@ __global__ void summary_kernel(const float *__restrict__ mx, const float *__rest
         } else if (STAT == 2) {
             out[i] = my[i];
         } else if (STAT == 3) {
-            out[i] = __fsub_rn(__fmul_rn(4.0f, clamp01(__fmul_rn(0.15f, rho[i]))), 0.5f);
+            out[i] = mul_sub(4.0f, clamp01(__fmul_rn(0.15f, rho[i])), 0.5f);
         } else {
-            const float s2 = __fadd_rn(__fmul_rn(mx[i], mx[i]), __fmul_rn(my[i], my[i]));
+            const float s2 = mul_add(mx[i], mx[i], __fmul_rn(my[i], my[i]));
             out[i] = __fsub_rn(clamp01(__fmul_rn(5.0f, __fsqrt_rn(s2))), 0.5f);
         }
     }
@@ -891,9 +891,9 @@ __global__ void color_map_kernel(const float *__restrict__ out, const uint8_t *_
             const float rw = __fadd_rn((float)(-block), c);
             const float lw = __fsub_rn(1.0f, rw);
             const float *A = c_cmap_nodes[map][block - ilo], *B = c_cmap_nodes[map][block - ilo + 1];
-            cr = __fadd_rn(__fmul_rn(lw, A[0]), __fmul_rn(rw, B[0]));
-            cg = __fadd_rn(__fmul_rn(lw, A[1]), __fmul_rn(rw, B[1]));
-            cb = __fadd_rn(__fmul_rn(lw, A[2]), __fmul_rn(rw, B[2]));
+            cr = mul_add(lw, A[0], __fmul_rn(rw, B[0]));
+            cg = mul_add(lw, A[1], __fmul_rn(rw, B[1]));
+            cb = mul_add(lw, A[2], __fmul_rn(rw, B[2]));
         } else {
             cr = c_cmap_nodes[map][nseg][0];
             cg = c_cmap_nodes[map][nseg][1];

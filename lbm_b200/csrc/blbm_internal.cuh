@@ -101,6 +101,25 @@ struct StepParams {
 // device row index of owned row r in [0, rows): one halo/guard row above
 __host__ __device__ inline size_t row_off(uint32_t r, uint32_t P) { return (size_t)(r + 1) * P; }
 
+// ---- contraction twin (-DBLBM_CONTRACT -> libblbm_contract.so) -----------------------------------
+// The default build rounds every multiply and every add separately (the defined parity semantics; what lavapipe
+// does).  Should a WebGPU backend that fuses ever be the parity target, the twin applies the rule an LLVM-style
+// backend applies to each shader after CSE — a multiply with exactly one use is fused into the add/sub that uses
+// it (left operand first when both are multiplies) — with explicit __fmaf_rn (still -fmad=false: nothing else
+// may fuse):
+//   corner_collision.wgsl    u2 = fma(ux, ux, uy*uy);  f += w*(k*(p-u215)-f)  ->  fma(w, fma(k, p-u215, -f), f)
+//   cardinal_collision.wgsl  the relaxations as above; u2 stays a plain sum there (ux2, uy2 have two uses each)
+//   rho.wgsl  fma(4, clamp(..), -0.5);  speed.wgsl  sqrt(fma(mx, mx, my*my));  color maps  fma(lw, A, rw*B)
+// ux3, uy3, uxuy2, u215, 4.5*(..), 4.5*ux2 have several uses after CSE and keep their own rounding.
+// tests/test_contract_twin.py runs the parity suite on the twin pair.
+#ifdef BLBM_CONTRACT
+__device__ __forceinline__ float mul_add(const float a, const float b, const float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float mul_sub(const float a, const float b, const float c) { return __fmaf_rn(a, b, -c); }
+#else
+__device__ __forceinline__ float mul_add(const float a, const float b, const float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+__device__ __forceinline__ float mul_sub(const float a, const float b, const float c) { return __fsub_rn(__fmul_rn(a, b), c); }
+#endif
+
 // ---- BGK collision of one cell, op-for-op the four collide passes -------------------------------
 // pre_collision/corner_pre_collision.wgsl:19-21, cardinal_pre_collision.wgsl:19-21,
 // collision/corner_collision.wgsl:24-42, cardinal_collision.wgsl:25-43.
@@ -136,23 +155,32 @@ __device__ __forceinline__ void collide_cell(float (&f)[8], float &rest, const f
     const float uxuy2 = __fmul_rn(__fmul_rn(2.0f, ux), uy);
     const float u2 = __fadd_rn(ux2, uy2);
     const float u215 = __fmul_rn(1.5f, u2);
+#ifdef BLBM_CONTRACT
+    // corner shader: ux2 and uy2 have one use each there, so u2 = fma(ux, ux, uy2); the cardinal shader uses both
+    // squares twice and keeps the plain sum above
+    const float u2c = __fmaf_rn(ux, ux, uy2);
+    const float u215c = __fmul_rn(1.5f, u2c);
+#else
+    const float u2c = u2, u215c = u215;
+#endif
     const float one_p_ux3 = __fadd_rn(1.0f, ux3);
     const float one_m_ux3 = __fsub_rn(1.0f, ux3);
-    const float q_pos = __fmul_rn(4.5f, __fadd_rn(u2, uxuy2));
-    const float q_neg = __fmul_rn(4.5f, __fsub_rn(u2, uxuy2));
-#define BLBM_RELAX(fi, k, poly) __fadd_rn(fi, __fmul_rn(omega, __fsub_rn(__fmul_rn(k, __fsub_rn(poly, u215)), fi)))
-    f[D_NE] = BLBM_RELAX(ne, k36, __fadd_rn(__fadd_rn(one_p_ux3, uy3), q_pos));
-    f[D_SE] = BLBM_RELAX(se, k36, __fadd_rn(__fsub_rn(one_p_ux3, uy3), q_neg));
-    f[D_NW] = BLBM_RELAX(nw, k36, __fadd_rn(__fadd_rn(one_m_ux3, uy3), q_neg));
-    f[D_SW] = BLBM_RELAX(sw, k36, __fadd_rn(__fsub_rn(one_m_ux3, uy3), q_pos));
+    const float q_pos = __fmul_rn(4.5f, __fadd_rn(u2c, uxuy2));
+    const float q_neg = __fmul_rn(4.5f, __fsub_rn(u2c, uxuy2));
+    // f += omega * (k * (poly - u215) - f): two multiplies, each consumed once (mul_sub / mul_add above)
+#define BLBM_RELAX(fi, k, poly, u215x) mul_add(omega, mul_sub(k, __fsub_rn(poly, u215x), fi), fi)
+    f[D_NE] = BLBM_RELAX(ne, k36, __fadd_rn(__fadd_rn(one_p_ux3, uy3), q_pos), u215c);
+    f[D_SE] = BLBM_RELAX(se, k36, __fadd_rn(__fsub_rn(one_p_ux3, uy3), q_neg), u215c);
+    f[D_NW] = BLBM_RELAX(nw, k36, __fadd_rn(__fadd_rn(one_m_ux3, uy3), q_neg), u215c);
+    f[D_SW] = BLBM_RELAX(sw, k36, __fadd_rn(__fsub_rn(one_m_ux3, uy3), q_pos), u215c);
     // cardinal collision
-    rest = __fadd_rn(rest, __fmul_rn(omega, __fsub_rn(__fmul_rn(k49, __fsub_rn(1.0f, u215)), rest)));
+    rest = BLBM_RELAX(rest, k49, 1.0f, u215);
     const float ax = __fmul_rn(4.5f, ux2);
     const float ay = __fmul_rn(4.5f, uy2);
-    f[D_E] = BLBM_RELAX(e, k9, __fadd_rn(one_p_ux3, ax));
-    f[D_W] = BLBM_RELAX(w, k9, __fadd_rn(one_m_ux3, ax));
-    f[D_N] = BLBM_RELAX(n, k9, __fadd_rn(__fadd_rn(1.0f, uy3), ay));
-    f[D_S] = BLBM_RELAX(s, k9, __fadd_rn(__fsub_rn(1.0f, uy3), ay));
+    f[D_E] = BLBM_RELAX(e, k9, __fadd_rn(one_p_ux3, ax), u215);
+    f[D_W] = BLBM_RELAX(w, k9, __fadd_rn(one_m_ux3, ax), u215);
+    f[D_N] = BLBM_RELAX(n, k9, __fadd_rn(__fadd_rn(1.0f, uy3), ay), u215);
+    f[D_S] = BLBM_RELAX(s, k9, __fadd_rn(__fsub_rn(1.0f, uy3), ay), u215);
 #undef BLBM_RELAX
 }
 
@@ -252,6 +280,11 @@ __device__ __forceinline__ void collide_pair(f32x2_t (&f)[8], f32x2_t &rest, con
 __device__ __forceinline__ void collide_quad_packed(float (&g)[4][8], float (&rr)[4], const float omega,
                                                     float (&mx)[4], float (&my)[4], float (&rho)[4])
 {
+#ifdef BLBM_CONTRACT
+    // the twin has no packed flavour (ptxas would have to keep add.f32x2 and fma apart): same results, scalar
+#pragma unroll
+    for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], omega, mx[q], my[q], rho[q]);
+#else
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         f32x2_t f[8], rest = pk2(rr[2 * h], rr[2 * h + 1]), pmx, pmy, prho;
@@ -265,6 +298,7 @@ __device__ __forceinline__ void collide_quad_packed(float (&g)[4][8], float (&rr
         upk2(pmy, my[2 * h], my[2 * h + 1]);
         upk2(prho, rho[2 * h], rho[2 * h + 1]);
     }
+#endif
 }
 
 // moments exactly as the two pre-collision passes leave them (no rest term): reset_to_equilibrium /

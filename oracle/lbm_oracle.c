@@ -53,6 +53,25 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* Contraction twin (-DLBM_CONTRACT -> liblbm_oracle_contract.so).  WGSL lets a backend fuse a multiply into the add
+ * or subtract that consumes it; naga emits no NoContraction.  The default build defines "no contraction" (what
+ * lavapipe's LLVM pipeline does: its NIR options lower ffma and gallivm sets no fast-math flags).  Should a backend
+ * that fuses ever be the parity target, this twin states the rule an LLVM-style backend applies per shader after
+ * CSE — a multiply with exactly ONE use is fused into the add/sub using it (left operand first when both are
+ * multiplies) — and libblbm_contract.so (csrc -DBLBM_CONTRACT) follows the same rule, so the pair is ready:
+ *   corner_collision.wgsl   u2 = fma(ux,ux,uy*uy);  f += w*(k*(p-u215)-f)  ->  fma(w, fma(k, p-u215, -f), f)
+ *   cardinal_collision.wgsl the relaxations as above; u2 stays unfused there (ux2, uy2 have two uses each)
+ *   rho.wgsl                fma(4, clamp(..), -0.5);   speed.wgsl  sqrt(fma(mx,mx,my*my))
+ *   color_map/{jet,viridis,inferno}.wgsl   fma(lw, A, rw*B)
+ * ux3, uy3, uxuy2, u215, 4.5*(..), 4.5*ux2 have several uses after CSE and stay separate roundings. */
+#ifdef LBM_CONTRACT
+#define MULADD(a, b, c) fmaf((a), (b), (c))
+#define MULSUB(a, b, c) fmaf((a), (b), -(c))
+#else
+#define MULADD(a, b, c) ((a) * (b) + (c))
+#define MULSUB(a, b, c) ((a) * (b) - (c))
+#endif
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -212,12 +231,13 @@ static void collide_corner(lbm_oracle *o, int c)
         float ux2 = thisux * thisux;
         float uy2 = thisuy * thisuy;
         float uxuy2 = (2.0f * thisux) * thisuy;
-        float u2 = ux2 + uy2;
+        float u2 = MULADD(thisux, thisux, uy2); /* default build: ux2 + uy2 */
+        (void)ux2;
         float u215 = 1.5f * u2;
-        ne[i] = ne[i] + omega * (one36thrho * ((((1.0f + ux3) + uy3) + 4.5f * (u2 + uxuy2)) - u215) - ne[i]);
-        se[i] = se[i] + omega * (one36thrho * ((((1.0f + ux3) - uy3) + 4.5f * (u2 - uxuy2)) - u215) - se[i]);
-        nw[i] = nw[i] + omega * (one36thrho * ((((1.0f - ux3) + uy3) + 4.5f * (u2 - uxuy2)) - u215) - nw[i]);
-        sw[i] = sw[i] + omega * (one36thrho * ((((1.0f - ux3) - uy3) + 4.5f * (u2 + uxuy2)) - u215) - sw[i]);
+        ne[i] = MULADD(omega, MULSUB(one36thrho, (((1.0f + ux3) + uy3) + 4.5f * (u2 + uxuy2)) - u215, ne[i]), ne[i]);
+        se[i] = MULADD(omega, MULSUB(one36thrho, (((1.0f + ux3) - uy3) + 4.5f * (u2 - uxuy2)) - u215, se[i]), se[i]);
+        nw[i] = MULADD(omega, MULSUB(one36thrho, (((1.0f - ux3) + uy3) + 4.5f * (u2 - uxuy2)) - u215, nw[i]), nw[i]);
+        sw[i] = MULADD(omega, MULSUB(one36thrho, (((1.0f - ux3) - uy3) + 4.5f * (u2 + uxuy2)) - u215, sw[i]), sw[i]);
     }
 }
 
@@ -240,11 +260,11 @@ static void collide_cardinal(lbm_oracle *o, int c)
         float uy2 = thisuy * thisuy;
         float u2 = ux2 + uy2;
         float u215 = 1.5f * u2;
-        origin[i] = origin[i] + omega * (((4.0f / 9.0f) * thisrho) * (1.0f - u215) - origin[i]);
-        e[i] = e[i] + omega * (one9thrho * (((1.0f + ux3) + 4.5f * ux2) - u215) - e[i]);
-        w[i] = w[i] + omega * (one9thrho * (((1.0f - ux3) + 4.5f * ux2) - u215) - w[i]);
-        n[i] = n[i] + omega * (one9thrho * (((1.0f + uy3) + 4.5f * uy2) - u215) - n[i]);
-        s[i] = s[i] + omega * (one9thrho * (((1.0f - uy3) + 4.5f * uy2) - u215) - s[i]);
+        origin[i] = MULADD(omega, MULSUB((4.0f / 9.0f) * thisrho, 1.0f - u215, origin[i]), origin[i]);
+        e[i] = MULADD(omega, MULSUB(one9thrho, ((1.0f + ux3) + 4.5f * ux2) - u215, e[i]), e[i]);
+        w[i] = MULADD(omega, MULSUB(one9thrho, ((1.0f - ux3) + 4.5f * ux2) - u215, w[i]), w[i]);
+        n[i] = MULADD(omega, MULSUB(one9thrho, ((1.0f + uy3) + 4.5f * uy2) - u215, n[i]), n[i]);
+        s[i] = MULADD(omega, MULSUB(one9thrho, ((1.0f - uy3) + 4.5f * uy2) - u215, s[i]), s[i]);
     }
 }
 
@@ -337,12 +357,12 @@ void lbm_oracle_summary(lbm_oracle *o, int stat)
         break;
     case STAT_RHO: /* rho.wgsl:24 */
 #pragma omp parallel for schedule(static)
-        for (int64_t i = 0; i < n; i++) out[i] = 4.0f * clamp01(0.15f * rho[i]) - 0.5f;
+        for (int64_t i = 0; i < n; i++) out[i] = MULSUB(4.0f, clamp01(0.15f * rho[i]), 0.5f);
         break;
     case STAT_SPEED: /* speed.wgsl:25 */
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < n; i++)
-            out[i] = clamp01(5.0f * sqrtf(mx[i] * mx[i] + my[i] * my[i])) - 0.5f;
+            out[i] = clamp01(5.0f * sqrtf(MULADD(mx[i], mx[i], my[i] * my[i]))) - 0.5f;
         break;
     default:
         break;
@@ -509,13 +529,23 @@ void lbm_oracle_color_map(const lbm_oracle *o, int map, float *rgb)
             const float rw = (float)(-block) + c; /* "4.0 + color", "3.0 + color", ... "-3.0 + color" */
             const float lw = 1.0f - rw;
             const float *A = nodes[block - ilo], *B = nodes[block - ilo + 1];
-            r = lw * A[0] + rw * B[0];
-            g = lw * A[1] + rw * B[1];
-            b = lw * A[2] + rw * B[2];
+            r = MULADD(lw, A[0], rw * B[0]);
+            g = MULADD(lw, A[1], rw * B[1]);
+            b = MULADD(lw, A[2], rw * B[2]);
         } else { /* default: the last node */
             r = nodes[nseg][0]; g = nodes[nseg][1]; b = nodes[nseg][2];
         }
         if (o->bar[i] == 1u) r = g = b = 0.0f;
         rgb[3 * i + 0] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
     }
+}
+
+/* 1 in the contraction twin (liblbm_oracle_contract.so), 0 in the default build */
+int lbm_oracle_contract(void)
+{
+#ifdef LBM_CONTRACT
+    return 1;
+#else
+    return 0;
+#endif
 }

@@ -12,7 +12,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liblbm_oracle.so")
+# LBM_ORACLE_CONTRACT=1 selects the contraction twin (see the header of lbm_oracle.c); the parity tests then pair it
+# with lbm_b200/libblbm_contract.so (BLBM_LIBRARY)
+CONTRACT = os.environ.get("LBM_ORACLE_CONTRACT", "0") not in ("", "0")
+_LIB_PATH = os.path.join(_HERE, "liblbm_oracle_contract.so" if CONTRACT else "liblbm_oracle.so")
 
 POP_NAMES = ("nw", "n", "ne", "w", "rest", "e", "sw", "s", "se")  # lbm.rs:632-640
 CURL, UX, UY, RHO, SPEED = range(5)  # lbm.rs:10-16
@@ -21,20 +24,23 @@ CURL, UX, UY, RHO, SPEED = range(5)  # lbm.rs:10-16
 def build(force=False):
     """Compile the C oracle in place (gcc, a second or two)."""
     src = os.path.join(_HERE, "lbm_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    twin = os.path.join(_HERE, "liblbm_oracle_contract.so")
+    if force or any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(src) for p in (_LIB_PATH, twin)):
         subprocess.run(["make", "-C", _HERE, "--no-print-directory"], check=True,
                        stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
+def lib(contract=None):
+    """the oracle library: the default build, or (contract=True / LBM_ORACLE_CONTRACT=1) the contraction twin"""
+    contract = CONTRACT if contract is None else bool(contract)
+    _lib = _libs.get(contract)
     if _lib is None:
         build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(os.path.join(_HERE, "liblbm_oracle_contract.so" if contract else "liblbm_oracle.so"))
         P = C.c_void_p
         L.lbm_oracle_create.restype = P
         L.lbm_oracle_create.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float]
@@ -61,7 +67,9 @@ def lib():
         L.lbm_oracle_compute_num.argtypes = [P]
         L.lbm_oracle_threads.restype = C.c_int
         L.lbm_oracle_set_threads.argtypes = [C.c_int]
-        _lib = L
+        L.lbm_oracle_contract.restype = C.c_int
+        assert bool(L.lbm_oracle_contract()) == contract
+        _libs[contract] = _lib = L
     return _lib
 
 
@@ -87,9 +95,9 @@ def use_all_cores():
 
 
 class Oracle:
-    def __init__(self, omega, x, y, inflow_ux=0.1):
+    def __init__(self, omega, x, y, inflow_ux=0.1, contract=None):
         self.w, self.h = int(x), int(y)
-        self._L = lib()
+        self._L = lib(contract)
         self._h = self._L.lbm_oracle_create(self.w, self.h, float(omega), float(inflow_ux))
         if not self._h:
             raise MemoryError("lbm_oracle_create failed")
