@@ -345,7 +345,7 @@ class Job:
             del m
         if args.block_rows:
             lbm.set_tuning(0, args.block_rows)
-        for knob, val in ((4, args.dense), (5, args.graphs), (6, args.packed), (7, args.index32)):
+        for knob, val in ((4, args.dense), (5, args.graphs), (6, args.packed), (7, args.index32), (8, args.link_in_kernel)):
             if val >= 0:
                 lbm.set_tuning(knob, val)
         return lbm, r0, r1
@@ -583,6 +583,8 @@ def main():
     ap.add_argument("--dense", type=int, default=-1, help="vec4 bounce flavour: -1 auto, 0 sparse, 1 dense, 2 dense + cp.async staging")
     ap.add_argument("--packed", type=int, default=-1, help="vec4 packed fp32 adds (FADD2): -1 default (off: measured slower), 0, 1")
     ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 auto, 0, 1")
+    ap.add_argument("--link-in-kernel", type=int, default=-1,
+                    help="linked slabs: halo epoch handshake inside the step kernel (1, default) or by wait/signal kernels (0)")
     ap.add_argument("--lazy", type=int, default=-1, help="barrier-chain table: 0 never, 1 always, 2 auto (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -645,7 +647,8 @@ def main():
         "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, n),
-        "implementation": {"kernel": kname,
+        "implementation": {"kernel": kname, "halo_handshake": (None if n == 1 else "wait/signal kernels" if args.link_in_kernel == 0
+                                                               else "inside the step kernel"),
                            "parallelism": (f"y-slabs x{n}, one blbm_create_group handle in one process" if job.single
                                            else f"y-slabs x{n}, one process per GPU (CUDA IPC peers)"),
                            "device_bytes_per_gpu": device_bytes // (n if job.single else 1)},

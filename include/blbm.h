@@ -151,7 +151,9 @@ int blbm_single_cell(blbm_t *h, uint32_t index);
 
 /* LBM::draw_shape -> draw_barrier_updates + barrier_draw.wgsl, lbm.rs:1337-1356: pairs is
  * [loc0, val0, loc1, val1, ...] as produced by get_points_vector (merge_shapes.rs:12-22); loc is a
- * GLOBAL cell index, val 1 = barrier, 0 = fluid; out-of-range locations are dropped.  Duplicate
+ * GLOBAL cell index, val 1 = barrier, anything else = fluid (stored as 0: barrier_draw.wgsl stores the raw value, but
+ * every consumer — the stream passes, the colour maps — only tests == 1, and the reference's own callers only ever
+ * produce 0 / 1; blbm_read_barrier therefore returns 0 / 1 words); out-of-range locations are dropped.  Duplicate
  * locations: last pair wins (the reference leaves it to the GPU's scatter order; Blob keys are unique).
  * npairs == 0 is a no-op (the reference underflows, lbm.rs:1343; its callers guard). */
 int blbm_draw_points(blbm_t *h, const uint32_t *loc_val_pairs, size_t npairs);

@@ -7,7 +7,9 @@
 // octant-transform formulation — map the segment into the first octant, walk x with error = dy - dx,
 // step y when error >= 0 — restated here from its published algorithm.  In the first octant that walk emits
 // y_k = floor(k*dy/dx), which is the closed form the tests check this walk against.
-// UNPINNED: neither the crate nor the reference can be run in this environment.
+// Pinned: Line::new / Line::new_erased as compiled into the reference's shipped wasm binary (the crate's Bresenham
+// included) were executed on 99 end-point pairs; blbm_rasterize_line reproduces every cell (tests/test_wasm_pin.py).
+// The presets' end-point arithmetic (lbm.rs:1367-1480) is inlined into the binary's event loop and stays a restatement.
 #include <algorithm>
 #include <cstdint>
 #include <set>

@@ -5,7 +5,9 @@ diagonal step; eraser = 59 segments) and the presets of lbm.rs:1367-1480.  The B
 un-vendored crate `line_drawing` 1.0.0 (Cargo.lock:679-680) is NOT transcribed here: in the first octant its
 "error = dy - dx, step y when error >= 0" loop emits y_k = floor(k*dy/dx), and this file uses that closed form
 (exact integer arithmetic) together with the crate's octant transforms — a different code path from the
-product's, so a slip in either shows up.  UNPINNED against the real crate, which is not available offline.
+product's, so a slip in either shows up.  Pinned: reproduces, cell for cell, Line::new / Line::new_erased as
+compiled (with the crate) into the reference's shipped wasm binary, on 99 end-point pairs (tests/test_wasm_pin.py,
+tests/golden/wasm_golden.npz).
 """
 
 

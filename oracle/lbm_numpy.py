@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/lbm_oracle.c).  Purpose: a different code path (whole-array
 slicing on zero-padded flat arrays instead of per-cell loops) that must agree BIT-FOR-BIT with the C
-oracle; a transcription slip in either shows up as a mismatch.  PARITY UNPINNED against the real
-reference, which cannot run here.
+oracle; a transcription slip in either shows up as a mismatch.  Parity status as for the C oracle: pinned
+to the reference's executed WGSL text and to its wasm binary's host functions, not to a WebGPU-backend run.
 
 numpy float32 arithmetic rounds every binary op individually (no FMA), `/` is IEEE division — the
 oracle semantics of SURVEY.md section 8.  Reference files: the same list as lbm_oracle.c
