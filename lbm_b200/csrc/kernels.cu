@@ -191,7 +191,7 @@ constexpr uint32_t GRID_Y = 32768;
 // LINKED: the epoch handshake with the neighbouring slabs runs inside the kernel (LinkSync); a separate instantiation
 // so that the unlinked kernel keeps its 64-register budget.
 template <bool MOM, int V4_ROWS, int DENSE, bool PACKED, typename IDX, bool LINKED = false>
-__global__ void __launch_bounds__(32 * V4_ROWS, (DENSE || LINKED) ? (MOM ? 768 : 1024) / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
+__global__ void __launch_bounds__(32 * V4_ROWS, (DENSE || LINKED || MOM) ? 1024 / (32 * V4_ROWS) : 0) step_vec4_kernel(const StepParams p)
 {
     constexpr bool STAGED = DENSE >= 2;
     constexpr bool EAGER_CLS = DENSE == 3;  // class words read up front, without the chunk-flag test

@@ -78,19 +78,17 @@ __device__ __forceinline__ void finish_group(const StepParams &p, const IDX i, c
     }
 
     float rr[4] = {vr.x, vr.y, vr.z, vr.w};
-    float mx[4], my[4], rho[4];
-    if (PACKED) {
-        collide_quad_packed(g, rr, p.omega, mx, my, rho);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], p.omega, mx[q], my[q], rho[q]);
-    }
-
-    // cells beyond the row end (ragged W) are padding: written, never read
-    stg4(p.R + i, make_float4(rr[0], rr[1], rr[2], rr[3]));
-#pragma unroll
-    for (int d = 0; d < 8; d++) stg4(p.Y[d] + i, make_float4(g[0][d], g[1][d], g[2][d], g[3][d]));
     if (MOM) {
+        // The moments of the pre-collision state — exactly the sums collide_cell() forms first — are computed and
+        // stored BEFORE the collision, so that twelve values do not stay live across it (the collision below forms
+        // the same sums again; the empty asm keeps the compiler from carrying them over).  64 registers, like the
+        // launches that store no moments.
+        float mx[4], my[4], rho[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            precollision_moments(g[q], mx[q], my[q], rho[q]);
+            rho[q] = __fadd_rn(rho[q], rr[q]);
+        }
         if (cany & CLS_CHAIN) {
             // chain cells: their plane slots are don't-care, the moments of their latest collide are in the table,
             // slot_e onwards in plane order (dead slots still count)
@@ -109,27 +107,48 @@ __device__ __forceinline__ void finish_group(const StepParams &p, const IDX i, c
         stg4(p.mx + i, make_float4(mx[0], mx[1], mx[2], mx[3]));
         stg4(p.my + i, make_float4(my[0], my[1], my[2], my[3]));
         stg4(p.rho + i, make_float4(rho[0], rho[1], rho[2], rho[3]));
+        // moment rows a neighbouring slab's curl stencil reads
+        if (r == 0 && p.push.up_n) {
+            stg4(p.push.up_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stg4(p.push.up_my + x4, make_float4(my[0], my[1], my[2], my[3]));
+        }
+        if (r == p.rows - 1 && p.push.dn_s) {
+            stg4(p.push.dn_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stg4(p.push.dn_my + x4, make_float4(my[0], my[1], my[2], my[3]));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            asm volatile("" : "+f"(rr[q]));
+#pragma unroll
+            for (int d = 0; d < 8; d++) asm volatile("" : "+f"(g[q][d]));
+        }
     }
+    {
+        float mx[4], my[4], rho[4];  // formed again by the collision; dead in every launch
+        if (PACKED) {
+            collide_quad_packed(g, rr, p.omega, mx, my, rho);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) collide_cell(g[q], rr[q], p.omega, mx[q], my[q], rho[q]);
+        }
+    }
+
+    // cells beyond the row end (ragged W) are padding: written, never read
+    stg4(p.R + i, make_float4(rr[0], rr[1], rr[2], rr[3]));
+#pragma unroll
+    for (int d = 0; d < 8; d++) stg4(p.Y[d] + i, make_float4(g[0][d], g[1][d], g[2][d], g[3][d]));
     // mirror the cells a neighbouring slab gathers from into its halo rows (NVLink stores)
     if (r == 0 && p.push.up_n) {
         stg4(p.push.up_n + x4, make_float4(g[0][D_N], g[1][D_N], g[2][D_N], g[3][D_N]));
         stg4(p.push.up_ne + x4, make_float4(g[0][D_NE], g[1][D_NE], g[2][D_NE], g[3][D_NE]));
         stg4(p.push.up_nw + x4, make_float4(g[0][D_NW], g[1][D_NW], g[2][D_NW], g[3][D_NW]));
         if (x4 == 0) p.push.up_w[0] = g[0][D_W];
-        if (MOM) {
-            stg4(p.push.up_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
-            stg4(p.push.up_my + x4, make_float4(my[0], my[1], my[2], my[3]));
-        }
     }
     if (r == 1 && x4 == 0 && p.push.up_nw2) p.push.up_nw2[0] = g[0][D_NW];
     if (r == p.rows - 1 && p.push.dn_s) {
         stg4(p.push.dn_s + x4, make_float4(g[0][D_S], g[1][D_S], g[2][D_S], g[3][D_S]));
         stg4(p.push.dn_se + x4, make_float4(g[0][D_SE], g[1][D_SE], g[2][D_SE], g[3][D_SE]));
         stg4(p.push.dn_sw + x4, make_float4(g[0][D_SW], g[1][D_SW], g[2][D_SW], g[3][D_SW]));
-        if (MOM) {
-            stg4(p.push.dn_mx + x4, make_float4(mx[0], mx[1], mx[2], mx[3]));
-            stg4(p.push.dn_my + x4, make_float4(my[0], my[1], my[2], my[3]));
-        }
     }
 }
 

@@ -136,10 +136,11 @@ def test_default_step_kernels_keep_their_register_budget_and_wide_accesses():
         c = counts[k]
         assert c["LDG.E.128"] >= 9 and c["STG.E.128"] >= 9 and c["SHFL"] >= 6 and not c["LDL"] and not c["STL"]
         assert (c["LDGSTS"] > 0) == (flavour == 2)
-    # the moment-storing launch (one per iterate) may use more registers but must not spill either
+    # the moment-storing launch (one per iterate) stores its moments before the collision: same occupancy, at most
+    # four block-uniform / address words on the stack
     for flavour in (0, 2):
         k = names[f"step_vec4_kernel<(bool)1, (int)4, (int){flavour}, (bool)0, u32, (bool)0>"]
-        assert int(res[k]["REG"]) <= 80 and int(res[k]["STACK"]) == 0
+        assert int(res[k]["REG"]) <= 64 and int(res[k]["STACK"]) <= 16, (flavour, res[k])
 
 
 def test_every_entry_point_rejects_a_null_handle_without_crashing():
