@@ -490,12 +490,13 @@ def north_star(job, sampler):
 def run_e2e(job, lbm, w, r0, r1, ncells_total, args, sampler):
     """End to end through the C ABI with host buffers: every frame = paint a stroke (H2D from pinned host memory),
     blbm_iterate(n) (n steps + summary), read the output field back (D2H into pinned host memory), as
-    lib.rs:108-199 does per redraw.  The number of frames does not depend on --steps: at least 8, so that the
-    double-buffered read-back is in its steady state."""
+    lib.rs:108-199 does per redraw.  The number of frames does not depend on --steps: at least 16, so that the
+    double-buffered read-back is in its steady state and the drain of the last copy (which nothing can hide) weighs
+    what it would in a running application."""
     torch = job.torch
     rows = r1 - r0
     fs = max(1, args.frame_steps)
-    frames = max(8, args.steps // fs)
+    frames = max(16, args.steps // fs)
     node, cpus = gpu_numa_cpus(job.local)
     keep_affinity = os.sched_getaffinity(0)
     if cpus and not job.single:

@@ -330,61 +330,68 @@ int run_summary(blbm *h)
     return BLBM_OK;
 }
 
-constexpr uint32_t GRAPH_CHUNK = 8;  // even, so a replay starts on the parity it was captured for
+constexpr uint32_t GRAPH_MAX = 64;  // steps per graph launch at most
+constexpr uint32_t GRAPH_MIN = 4;   // shorter runs are launched directly
 
 bool graphs_wanted(const blbm *h)
 {
-    if (any_peer(h)) return false;  // peers: per-step handshake kernels
+    if (any_peer(h)) return false;  // peers: the epochs of the halo handshake are launch parameters
     if (h->use_graphs >= 0) return h->use_graphs != 0;
     return (unsigned long long)h->rows * h->W <= (4ull << 20);
 }
 
-// GRAPH_CHUNK fused, non-moment-storing steps starting at the current parity, as one graph launch
-int run_step_graph(blbm *h)
+// `count` fused, non-moment-storing steps starting at the current parity, as one graph launch
+int run_step_graph(blbm *h, uint32_t count)
 {
     const int par = (int)(h->step % 2);
-    blbm::StepGraph &g = h->graph[par];
     unsigned int omega_bits;
     memcpy(&omega_bits, &h->omega, sizeof(omega_bits));
-    const unsigned long long sig[4] = {
-        1ull + (unsigned long long)h->cls_cur, omega_bits,
+    const unsigned long long sig[5] = {
+        1ull + (unsigned long long)h->cls_cur + 2ull * (unsigned long long)par, omega_bits,
         (unsigned long long)h->kernel | ((unsigned long long)h->vec4_rows << 8) |
             ((unsigned long long)(h->vec4_dense + 1) << 16) | ((unsigned long long)h->chain_active << 24) |
             ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)(h->vec4_index32 + 1) << 26),
-        (unsigned long long)(uintptr_t)h->pool};
-    if (!g.exec || memcmp(g.sig, sig, sizeof(sig)) != 0) {
-        if (g.exec) {
-            cudaGraphExecDestroy(g.exec);
-            g.exec = nullptr;
+        (unsigned long long)(uintptr_t)h->pool, count};
+    blbm::StepGraph *g = nullptr, *victim = &h->graph[0];
+    for (blbm::StepGraph &c : h->graph) {
+        if (c.exec && memcmp(c.sig, sig, sizeof(sig)) == 0) g = &c;
+        if (!c.exec || (victim->exec && c.used < victim->used)) victim = &c;
+    }
+    if (!g) {
+        g = victim;
+        if (g->exec) {
+            cudaGraphExecDestroy(g->exec);
+            g->exec = nullptr;
         }
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int rc = BLBM_OK;
         const uint64_t step0 = h->step;
-        for (uint32_t q = 0; q < GRAPH_CHUNK && rc == BLBM_OK; q++) {
+        for (uint32_t q = 0; q < count && rc == BLBM_OK; q++) {
             const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
             rc = launch_step(h, MODE_FUSED, x, y, false);
             h->step++;
         }
         h->step = step0;
-        h->launches -= GRAPH_CHUNK;  // capture enqueues nothing
+        h->launches -= count;  // capture enqueues nothing
         cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
         if (rc != BLBM_OK) {
             if (graph) cudaGraphDestroy(graph);
             return rc;
         }
         if (e != cudaSuccess) return fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        e = cudaGraphInstantiate(&g->exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) {
-            g.exec = nullptr;
+            g->exec = nullptr;
             return fail(BLBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
         }
-        memcpy(g.sig, sig, sizeof(sig));
+        memcpy(g->sig, sig, sizeof(sig));
     }
-    CK(cudaGraphLaunch(g.exec, h->stream));
-    h->step += GRAPH_CHUNK;
-    h->launches += GRAPH_CHUNK;
+    g->used = ++h->graph_clock;
+    CK(cudaGraphLaunch(g->exec, h->stream));
+    h->step += count;
+    h->launches += count;
     return BLBM_OK;
 }
 
@@ -406,9 +413,11 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
             h->chain_unsettle = false;
             replayed = true;
         }
-        if (graphs && h->regimeT && !h->cls_pending && left > GRAPH_CHUNK) {
-            if ((rc = run_step_graph(h)) != BLBM_OK) return rc;
-            left -= GRAPH_CHUNK;
+        // every step but the call's last (it may store moments) can go into a graph
+        const uint32_t run = std::min(left - 1, GRAPH_MAX);
+        if (graphs && h->regimeT && !h->cls_pending && run >= GRAPH_MIN) {
+            if ((rc = run_step_graph(h, run)) != BLBM_OK) return rc;
+            left -= run;
             continue;
         }
         if (!h->regimeT) {
@@ -869,8 +878,8 @@ int blbm_destroy(blbm_t *h)
         stream_free(h->chain_state, h->stream);
         cudaStreamSynchronize(h->stream);
     }
-    for (int q = 0; q < 2; q++)
-        if (h->graph[q].exec) cudaGraphExecDestroy(h->graph[q].exec);
+    for (blbm::StepGraph &g : h->graph)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->mailbox_host) cudaFreeHost(h->mailbox_host);
     if (h->stage_host) cudaFreeHost(h->stage_host);
     for (int q = 0; q < blbm::STAGE_SLOTS; q++)
