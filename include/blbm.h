@@ -10,7 +10,14 @@
  *   - Every call returns BLBM_OK (0) or a negative blbm_status; blbm_last_error() gives the text of
  *     the last failure on the calling thread.  The reference panics instead (expect/unwrap).
  *   - A handle is not thread-safe (the reference's mutators take &mut self, single-threaded wasm).
- *   - Mutators enqueue on the handle's stream and return; blbm_read_* and blbm_synchronize wait.
+ *   - Mutators enqueue on the handle's stream and return; blbm_read_* and blbm_synchronize wait.  Paint lists of up
+ *     to 8192 pairs go through a pinned staging ring, so a frame loop of draw_points -> iterate -> read_output_async
+ *     never synchronises the host.  Two calls wait for the stream by design: blbm_write_barrier_rows (the caller's
+ *     buffer is free on return) and the first blbm_iterate / blbm_advance after creation, a whole-mask rewrite or a
+ *     paint of >= 1 % of the cells, which reads back one 8-byte count to decide whether barrier cells move to the
+ *     compact chain table (blbm_set_lazy_barriers).
+ *   - BLBM_EPEER (a linked neighbour did not reach the expected halo epoch within 20 s) is terminal: steps enqueued
+ *     after the time-out ran on stale halo rows and pushed their results on; destroy the linked handles.
  *   - Host buffers passed in are copied before the call returns (like queue.write_buffer,
  *     lbm.rs:1342-1343); the caller keeps ownership.
  *   - Cell index i = x + y*W, y = 0 is the top row, north = -W, east = +1 (lbm.rs:607-609).
