@@ -413,8 +413,8 @@ def multi_gpu_parity(job):
 
     lbm, r0, r1 = job.lattice(w, h, omega, u0, "porous", discs)
     run(lbm)
+    chain = lbm.lazy_barriers_active()  # (before the read-backs: reading populations returns the table to the planes)
     mine = state_digests(lbm, ranges if job.single else [(r0, r1)])
-    chain = lbm.lazy_barriers_active()
     job.barrier(lbm)
     lbm.close()
     got = mine if job.single else [d[0] for d in job.gather(mine)]
