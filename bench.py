@@ -441,14 +441,27 @@ def multi_gpu_parity(job):
     return res
 
 
-def time_workload(job, name, steps, warmup, sampler, part=None):
-    """one timed pass of a workload on this job's GPUs (or, part=(0, 1), on rank 0's GPU alone)"""
+def field_digests(lbm, row_ranges):
+    """sha256 of the density and of the curl output, per row range (full-size lattices: two planes, not twenty-two)"""
+    rho = lbm.read_density()
+    out = lbm.read_output()
+    base = lbm.row_begin
+    return [[sha(rho[a - base:b - base]), sha(out[a - base:b - base])] for a, b in row_ranges]
+
+
+def time_workload(job, name, steps, warmup, sampler, part=None, digest_steps=0, digest_ranges=None):
+    """one timed pass of a workload on this job's GPUs (or, part=(0, 1), on rank 0's GPU alone).  digest_steps > 0:
+    after that many steps from the initial state, sha256 of density and curl per row range go into the result."""
     w, rows_gpu, omega, u0, kind = WORKLOADS[name]
     strong = name in STRONG
     n = job.ngpu if part is None else part[1]
     h_total = rows_gpu if strong else rows_gpu * n
     lbm, r0, r1 = job.lattice(w, h_total, omega, u0, kind, part=part)
     ncells_gpu = w * (h_total // n)
+    digests = None
+    if digest_steps:
+        lbm.iterate(digest_steps)
+        digests = field_digests(lbm, digest_ranges if digest_ranges is not None else [(r0, r1)])
     w0 = len(sampler.windows)
     if part is None:
         t = timed_steps(job, lbm, w * h_total, ncells_gpu, steps, warmup, sampler)
@@ -458,10 +471,13 @@ def time_workload(job, name, steps, warmup, sampler, part=None):
         t = timed_steps(solo, lbm, w * h_total, ncells_gpu, steps, warmup, sampler)
     lbm.synchronize()
     lbm.close()
-    return {"workload": name, "W": w, "H": h_total, "n_gpus": n, "steps": steps, "warmup": warmup,
-            "value": t["value"], "unit": "MLUPS", "ms_per_step": t["ms"] / steps,
-            "frac": t["achieved"] / t["peak"], "achieved_gbs_per_gpu": t["achieved"],
-            "clocks": sampler.summary(sampler.windows[w0:])}
+    res = {"workload": name, "W": w, "H": h_total, "n_gpus": n, "steps": steps, "warmup": warmup,
+           "value": t["value"], "unit": "MLUPS", "ms_per_step": t["ms"] / steps,
+           "frac": t["achieved"] / t["peak"], "achieved_gbs_per_gpu": t["achieved"],
+           "clocks": sampler.summary(sampler.windows[w0:])}
+    if digests is not None:
+        res["_digests"] = digests
+    return res
 
 
 def north_star(job, sampler):
@@ -473,12 +489,23 @@ def north_star(job, sampler):
     ws["scaling"] = "weak (65536 x 8192 per GPU)"
     out["channel65536"] = ws
     job.barrier()
+    # parity at full size: after 20 steps from the initial state, density and curl of the N slabs against the same rows
+    # of the undivided 32768^2 lattice (1.07 G cells) on rank 0's GPU
+    from lbm_b200.lbm import slab_rows
+    h32 = WORKLOADS["cylinder32768"][1]
+    ranges = slab_rows(h32, job.ngpu)
     t1 = None
     if job.rank == 0:
-        t1 = time_workload(job, "cylinder32768", 40, 4, sampler, part=(0, 1))
+        t1 = time_workload(job, "cylinder32768", 40, 4, sampler, part=(0, 1), digest_steps=20, digest_ranges=ranges)
     job.barrier()
-    tn = time_workload(job, "cylinder32768", 100, 10, sampler)
+    tn = time_workload(job, "cylinder32768", 100, 10, sampler, digest_steps=20,
+                       digest_ranges=ranges if job.single else None)
     t1 = job.gather(t1)[0]
+    got = tn.pop("_digests")
+    got = got if job.single else [d[0] for d in job.gather(got)]
+    want = t1.pop("_digests")
+    tn["parity_at_size"] = {"bit_identical": got == want, "cells": WORKLOADS["cylinder32768"][0] * h32, "steps": 20,
+                            "compared": "sha256 of density and curl output per slab vs the undivided lattice on one GPU"}
     tn["scaling"] = "strong"
     tn["t1_ms_per_step"] = t1["ms_per_step"]
     tn["t1_value"] = t1["value"]
@@ -660,6 +687,10 @@ def main():
     want_ns = args.north_star == 1 or (args.north_star < 0 and n == 8 and args.workload == "porous16384")
     if want_ns and n > 1:
         line["north_star"] = north_star(job, sampler)
+        if not line["north_star"]["cylinder32768"]["parity_at_size"]["bit_identical"]:
+            if job.rank == 0:
+                print(json.dumps({"error": "multi-GPU parity at full size failed", "north_star": line["north_star"]}))
+            raise SystemExit(3)
     sampler.stop()
     if job.rank == 0 and n == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, omega, u0, kind)

@@ -346,6 +346,12 @@ class LBM:
         _check(self._L.blbm_read_moments(self._h, mx.ctypes.data, my.ctypes.data, rho.ctypes.data))
         return mx, my, rho
 
+    def read_density(self):
+        """the density plane alone (blbm_read_moments with the two momentum pointers NULL)"""
+        rho = np.empty(self._shape(), np.float32)
+        _check(self._L.blbm_read_moments(self._h, None, None, rho.ctypes.data))
+        return rho
+
     def read_output(self):
         out = np.empty(self._shape(), np.float32)
         _check(self._L.blbm_read_output(self._h, out.ctypes.data))
