@@ -330,8 +330,7 @@ int run_summary(blbm *h)
     return BLBM_OK;
 }
 
-constexpr uint32_t GRAPH_MAX = 64;  // steps per graph launch at most
-constexpr uint32_t GRAPH_MIN = 4;   // shorter runs are launched directly
+constexpr uint32_t GRAPH_LEN[blbm::GRAPH_SIZES] = {16, 8, 4, 2};  // all even: a call's runs share one start parity
 
 bool graphs_wanted(const blbm *h)
 {
@@ -340,58 +339,82 @@ bool graphs_wanted(const blbm *h)
     return (unsigned long long)h->rows * h->W <= (4ull << 20);
 }
 
-// `count` fused, non-moment-storing steps starting at the current parity, as one graph launch
-int run_step_graph(blbm *h, uint32_t count)
+void drop_step_graphs(blbm *h)
 {
-    const int par = (int)(h->step % 2);
+    for (auto &par : h->graph)
+        for (auto &cls : par)
+            for (cudaGraphExec_t &g : cls)
+                if (g) {
+                    cudaGraphExecDestroy(g);
+                    g = nullptr;
+                }
+    h->graphs_primed = false;
+}
+
+// capture every run length for both start parities and both class buffers under the current kernel configuration
+int prime_step_graphs(blbm *h)
+{
+    drop_step_graphs(h);
+    const uint64_t step0 = h->step, launches0 = h->launches;
+    const int cls0 = h->cls_cur;
+    int rc = BLBM_OK;
+    for (int par = 0; par < 2 && rc == BLBM_OK; par++)
+        for (int cls = 0; cls < 2 && rc == BLBM_OK; cls++)
+            for (int q = 0; q < blbm::GRAPH_SIZES && rc == BLBM_OK; q++) {
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+                if (e != cudaSuccess) {
+                    rc = fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
+                    break;
+                }
+                h->step = (uint64_t)par;
+                h->cls_cur = cls;
+                for (uint32_t k = 0; k < GRAPH_LEN[q] && rc == BLBM_OK; k++) {
+                    const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
+                    rc = launch_step(h, MODE_FUSED, x, y, false);
+                    h->step++;
+                }
+                e = cudaStreamEndCapture(h->stream, &graph);
+                if (rc == BLBM_OK && e != cudaSuccess) rc = fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
+                if (rc == BLBM_OK) {
+                    e = cudaGraphInstantiate(&h->graph[par][cls][q], graph, 0);
+                    if (e != cudaSuccess) {
+                        h->graph[par][cls][q] = nullptr;
+                        rc = fail(BLBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+                    }
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+    h->step = step0;
+    h->cls_cur = cls0;
+    h->launches = launches0;  // capture enqueues nothing
+    if (rc != BLBM_OK) {
+        drop_step_graphs(h);
+        return rc;
+    }
+    h->graphs_primed = true;
+    return BLBM_OK;
+}
+
+// GRAPH_LEN[q] fused, non-moment-storing steps starting at the current parity, as one graph launch
+int run_step_graph(blbm *h, int q)
+{
     unsigned int omega_bits;
     memcpy(&omega_bits, &h->omega, sizeof(omega_bits));
-    const unsigned long long sig[5] = {
-        1ull + (unsigned long long)h->cls_cur + 2ull * (unsigned long long)par, omega_bits,
+    const unsigned long long sig[4] = {
+        1, omega_bits,
         (unsigned long long)h->kernel | ((unsigned long long)h->vec4_rows << 8) |
             ((unsigned long long)(h->vec4_dense + 1) << 16) | ((unsigned long long)h->chain_active << 24) |
             ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)(h->vec4_index32 + 1) << 26),
-        (unsigned long long)(uintptr_t)h->pool, count};
-    blbm::StepGraph *g = nullptr, *victim = &h->graph[0];
-    for (blbm::StepGraph &c : h->graph) {
-        if (c.exec && memcmp(c.sig, sig, sizeof(sig)) == 0) g = &c;
-        if (!c.exec || (victim->exec && c.used < victim->used)) victim = &c;
+        (unsigned long long)(uintptr_t)h->pool};
+    if (!h->graphs_primed || memcmp(h->graph_sig, sig, sizeof(sig)) != 0) {
+        const int rc = prime_step_graphs(h);
+        if (rc != BLBM_OK) return rc;
+        memcpy(h->graph_sig, sig, sizeof(sig));
     }
-    if (!g) {
-        g = victim;
-        if (g->exec) {
-            cudaGraphExecDestroy(g->exec);
-            g->exec = nullptr;
-        }
-        cudaGraph_t graph = nullptr;
-        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = BLBM_OK;
-        const uint64_t step0 = h->step;
-        for (uint32_t q = 0; q < count && rc == BLBM_OK; q++) {
-            const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
-            rc = launch_step(h, MODE_FUSED, x, y, false);
-            h->step++;
-        }
-        h->step = step0;
-        h->launches -= count;  // capture enqueues nothing
-        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-        if (rc != BLBM_OK) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
-        }
-        if (e != cudaSuccess) return fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&g->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) {
-            g->exec = nullptr;
-            return fail(BLBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-        }
-        memcpy(g->sig, sig, sizeof(sig));
-    }
-    g->used = ++h->graph_clock;
-    CK(cudaGraphLaunch(g->exec, h->stream));
-    h->step += count;
-    h->launches += count;
+    CK(cudaGraphLaunch(h->graph[h->step % 2][h->cls_cur][q], h->stream));
+    h->step += GRAPH_LEN[q];
+    h->launches += GRAPH_LEN[q];
     return BLBM_OK;
 }
 
@@ -414,10 +437,11 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
             replayed = true;
         }
         // every step but the call's last (it may store moments) can go into a graph
-        const uint32_t run = std::min(left - 1, GRAPH_MAX);
-        if (graphs && h->regimeT && !h->cls_pending && run >= GRAPH_MIN) {
-            if ((rc = run_step_graph(h, run)) != BLBM_OK) return rc;
-            left -= run;
+        if (graphs && h->regimeT && !h->cls_pending && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
+            int q = 0;
+            while (GRAPH_LEN[q] > left - 1) q++;
+            if ((rc = run_step_graph(h, q)) != BLBM_OK) return rc;
+            left -= GRAPH_LEN[q];
             continue;
         }
         if (!h->regimeT) {
@@ -878,8 +902,7 @@ int blbm_destroy(blbm_t *h)
         stream_free(h->chain_state, h->stream);
         cudaStreamSynchronize(h->stream);
     }
-    for (blbm::StepGraph &g : h->graph)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
+    drop_step_graphs(h);
     if (h->mailbox_host) cudaFreeHost(h->mailbox_host);
     if (h->stage_host) cudaFreeHost(h->stage_host);
     for (int q = 0; q < blbm::STAGE_SLOTS; q++)

@@ -121,16 +121,15 @@ struct blbm_handle {
     bool chain_unsettle = false;       // omega changed: settled chains must be recomputed by the next replay
     unsigned long long *chain_counter = nullptr;
     unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
-    // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): runs of fused, non-moment-storing steps
-    // are captured once into a CUDA graph per (start parity, length, class buffer, kernel shape) and replayed; a small
-    // LRU holds the shapes a frame loop cycles through (iterate(15) with a paint per frame: two of them).
-    static constexpr int GRAPH_SLOTS = 8;
-    struct StepGraph {
-        cudaGraphExec_t exec = nullptr;
-        unsigned long long sig[5] = {0, 0, 0, 0, 0};
-        uint64_t used = 0;  // LRU stamp
-    } graph[GRAPH_SLOTS];
-    uint64_t graph_clock = 0;
+    // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): runs of 16, 8, 4 and 2 fused,
+    // non-moment-storing steps are captured into CUDA graphs — all four lengths for both start parities and both
+    // class buffers at once, the first time a run is wanted (about a millisecond, in the caller's first iterate), so
+    // that no capture ever lands inside a frame loop — and re-captured when omega, the kernel shape or the chain
+    // table change.
+    static constexpr int GRAPH_SIZES = 4;  // 16, 8, 4, 2
+    cudaGraphExec_t graph[2][2][GRAPH_SIZES] = {};  // [start parity][class buffer][length index]
+    unsigned long long graph_sig[4] = {0, 0, 0, 0};
+    bool graphs_primed = false;
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
     float *rgb = nullptr;  // colour buffer (rows x W x 3), allocated by the first blbm_color_map
 };
