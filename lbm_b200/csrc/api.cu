@@ -396,8 +396,8 @@ int prime_step_graphs(blbm *h)
     return BLBM_OK;
 }
 
-// GRAPH_LEN[q] fused, non-moment-storing steps starting at the current parity, as one graph launch
-int run_step_graph(blbm *h, int q)
+// (re)capture the graphs if the kernel configuration changed since they were made
+int ensure_step_graphs(blbm *h)
 {
     unsigned int omega_bits;
     memcpy(&omega_bits, &h->omega, sizeof(omega_bits));
@@ -412,6 +412,12 @@ int run_step_graph(blbm *h, int q)
         if (rc != BLBM_OK) return rc;
         memcpy(h->graph_sig, sig, sizeof(sig));
     }
+    return BLBM_OK;
+}
+
+// GRAPH_LEN[q] fused, non-moment-storing steps starting at the current parity, as one graph launch
+int run_step_graph(blbm *h, int q)
+{
     CK(cudaGraphLaunch(h->graph[h->step % 2][h->cls_cur][q], h->stream));
     h->step += GRAPH_LEN[q];
     h->launches += GRAPH_LEN[q];
@@ -436,7 +442,10 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
             h->chain_unsettle = false;
             replayed = true;
         }
-        // every step but the call's last (it may store moments) can go into a graph
+        // every step but the call's last (it may store moments) can go into a graph; the graphs are made (or re-made
+        // after a change of omega / kernel shape / chain table) by the first call that could use one, however short,
+        // so that the millisecond of capturing lands in a caller's warm-up and never in the middle of a frame loop
+        if (graphs && h->regimeT && (rc = ensure_step_graphs(h)) != BLBM_OK) return rc;
         if (graphs && h->regimeT && !h->cls_pending && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
             int q = 0;
             while (GRAPH_LEN[q] > left - 1) q++;
