@@ -186,6 +186,10 @@ int blbm_rasterize_line(int64_t x1, int64_t y1, int64_t x2, int64_t y2, int64_t 
 int blbm_draw_line(blbm_t *h, int64_t x1, int64_t y1, int64_t x2, int64_t y2);
 int blbm_erase_line(blbm_t *h, int64_t x1, int64_t y1, int64_t x2, int64_t y2);
 /* LBM::curl_barrier / chaos_barrier / welcome_barrier, lbm.rs:1367-1480 (callers reset_barrier first, lib.rs:120-128) */
+typedef enum blbm_preset { BLBM_PRESET_CURL = 0, BLBM_PRESET_CHAOS = 1, BLBM_PRESET_WELCOME = 2 } blbm_preset;
+/* The end points (x1, y1, x2, y2 per line, in the order the reference creates them) of the thick lines a preset
+ * consists of on an xdim x ydim lattice; count = number of lines.  Pure host code: works without a GPU. */
+int blbm_preset_lines(int preset, int64_t xdim, int64_t ydim, int64_t *xyxy, size_t capacity, size_t *count);
 int blbm_curl_barrier(blbm_t *h);
 int blbm_chaos_barrier(blbm_t *h);
 int blbm_welcome_barrier(blbm_t *h);

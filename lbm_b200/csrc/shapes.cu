@@ -9,7 +9,9 @@
 // y_k = floor(k*dy/dx), which is the closed form the tests check this walk against.
 // Pinned: Line::new / Line::new_erased as compiled into the reference's shipped wasm binary (the crate's Bresenham
 // included) were executed on 99 end-point pairs; blbm_rasterize_line reproduces every cell (tests/test_wasm_pin.py).
-// The presets' end-point arithmetic (lbm.rs:1367-1480) is inlined into the binary's event loop and stays a restatement.
+// The presets (lbm.rs:1367-1480) are inlined into the binary's event-loop closure; their `match` arms were executed
+// in place (fragment execution from the arm's first instruction): blbm_preset_lines reproduces every Line::new
+// argument and the painted masks equal the point sets the binary hands to draw_shape (tests/golden/wasm_presets.npz).
 #include <algorithm>
 #include <cstdint>
 #include <set>
@@ -200,84 +202,120 @@ int blbm_erase_line(blbm_t *h, int64_t x1, int64_t y1, int64_t x2, int64_t y2)
     return draw_set(h, pts, (uint64_t)x, 0);
 }
 
-// LBM::curl_barrier, lbm.rs:1367-1370
-int blbm_curl_barrier(blbm_t *h)
+// The end points of the thick lines a preset is made of, in the order the reference creates them
+// (LBM::curl_barrier lbm.rs:1367-1370, chaos_barrier :1372-1386, welcome_barrier :1388-1480; isize arithmetic:
+// `/` truncates toward zero).  Pinned, argument for argument, against the Line::new calls of the reference's shipped
+// binary executing these very `match` arms of its event loop (tests/golden/wasm_presets.npz).
+int blbm_preset_lines(int preset, int64_t X, int64_t Y, int64_t *xyxy, size_t capacity, size_t *count)
 {
-    int64_t x, y;
-    int rc = geometry(h, &x, &y);
-    if (rc) return rc;
-    return blbm_draw_line(h, 4 * x / 10, y / 4, 4 * x / 10, y / 2);
+    std::vector<int64_t> v;
+    try {
+        auto line = [&](int64_t ax, int64_t ay, int64_t bx, int64_t by) {
+            v.push_back(ax);
+            v.push_back(ay);
+            v.push_back(bx);
+            v.push_back(by);
+        };
+        if (preset == BLBM_PRESET_CURL) {
+            line(4 * X / 10, Y / 4, 4 * X / 10, Y / 2);
+        } else if (preset == BLBM_PRESET_CHAOS) {
+            line(X / 2, 9 * Y / 20, X / 2, 0);
+            line(X / 2, 11 * Y / 20, X / 2, Y - 1);
+            line(3 * X / 5, Y / 2, 3 * X / 4, 3 * Y / 4);
+            line(3 * X / 5, Y / 2, 3 * X / 4, Y / 4);
+        } else if (preset == BLBM_PRESET_WELCOME) {
+            const int64_t height = -1 * (Y / 4), bottom = Y / 2, space = X / 50, lw = X / 13;
+            int64_t cx = X / 5;
+            // W
+            line(cx, bottom + height, cx, bottom);
+            line(cx, bottom, cx + lw / 2, bottom + height / 2);
+            cx += lw / 2;
+            line(cx, bottom + height / 2, cx + lw / 2, bottom);
+            cx += lw / 2;
+            line(cx, bottom + height, cx, bottom);
+            cx += space;
+            auto letter_e = [&]() {
+                line(cx, bottom + height / 2, cx, bottom);
+                line(cx, bottom, cx + lw, bottom);
+                line(cx, bottom + height / 4, cx + lw, bottom + height / 4);
+                line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
+                line(cx + lw, bottom + height / 2, cx + lw, bottom + height / 4);
+                cx += lw + space;
+            };
+            letter_e();
+            // l
+            line(cx, bottom, cx, bottom + height);
+            cx += space;
+            // c
+            line(cx, bottom + height / 2, cx, bottom);
+            line(cx, bottom, cx + lw, bottom);
+            line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
+            cx += lw + space;
+            // o
+            line(cx, bottom + height / 2, cx, bottom);
+            line(cx, bottom, cx + lw, bottom);
+            line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
+            line(cx + lw, bottom + height / 2, cx + lw, bottom);
+            cx += lw + space;
+            // m
+            line(cx, bottom + height / 2, cx, bottom);
+            line(cx + lw / 2, bottom, cx + lw / 2, bottom + height / 2);
+            line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
+            line(cx + lw, bottom + height / 2, cx + lw, bottom);
+            cx += lw + space;
+            letter_e();
+            // !
+            line(cx, height / 10 + bottom, cx, bottom);
+            line(cx, height / 5 + bottom, cx, bottom + height);
+        } else {
+            return BLBM_EINVAL;
+        }
+    } catch (...) {
+        return BLBM_ENOMEM;
+    }
+    if (count) *count = v.size() / 4;
+    for (size_t q = 0; q < v.size() && q < 4 * capacity; q++) xyxy[q] = v[q];
+    return BLBM_OK;
 }
 
-// LBM::chaos_barrier, lbm.rs:1372-1386: four separate draw_shape calls
-int blbm_chaos_barrier(blbm_t *h)
+static int preset_end_points(blbm_t *h, int preset, int64_t *X, int64_t *Y, std::vector<int64_t> *v)
 {
-    int64_t x, y;
-    int rc = geometry(h, &x, &y);
+    int rc = geometry(h, X, Y);
     if (rc) return rc;
-    if ((rc = blbm_draw_line(h, x / 2, 9 * y / 20, x / 2, 0))) return rc;
-    if ((rc = blbm_draw_line(h, x / 2, 11 * y / 20, x / 2, y - 1))) return rc;
-    if ((rc = blbm_draw_line(h, 3 * x / 5, y / 2, 3 * x / 4, 3 * y / 4))) return rc;
-    return blbm_draw_line(h, 3 * x / 5, y / 2, 3 * x / 4, y / 4);
+    size_t n = 0;
+    if ((rc = blbm_preset_lines(preset, *X, *Y, nullptr, 0, &n))) return rc;
+    try {
+        v->resize(4 * n);
+    } catch (...) {
+        return BLBM_ENOMEM;
+    }
+    return blbm_preset_lines(preset, *X, *Y, v->data(), n, &n);
 }
 
-// LBM::welcome_barrier, lbm.rs:1388-1480: "Welcome!" out of thick lines, joined into one Blob, drawn once
+// LBM::curl_barrier (one draw_shape) and LBM::chaos_barrier (four separate draw_shape calls)
+static int draw_preset_lines(blbm_t *h, int preset)
+{
+    int64_t X, Y;
+    std::vector<int64_t> v;
+    int rc = preset_end_points(h, preset, &X, &Y, &v);
+    for (size_t q = 0; q + 3 < v.size() && rc == BLBM_OK; q += 4) rc = blbm_draw_line(h, v[q], v[q + 1], v[q + 2], v[q + 3]);
+    return rc;
+}
+
+int blbm_curl_barrier(blbm_t *h) { return draw_preset_lines(h, BLBM_PRESET_CURL); }
+int blbm_chaos_barrier(blbm_t *h) { return draw_preset_lines(h, BLBM_PRESET_CHAOS); }
+
+// LBM::welcome_barrier: "Welcome!" out of thick lines, joined into one Blob, drawn once
 int blbm_welcome_barrier(blbm_t *h)
 {
     int64_t X, Y;
-    int rc = geometry(h, &X, &Y);
+    std::vector<int64_t> v;
+    int rc = preset_end_points(h, BLBM_PRESET_WELCOME, &X, &Y, &v);
     if (rc) return rc;
     std::set<Pt> blob;
-    bool ok = true;
-    auto line = [&](int64_t ax, int64_t ay, int64_t bx, int64_t by) {
-        ok = ok && line_points(Pt(ax, ay), Pt(bx, by), X, Y, false, &blob);
-    };
-    const int64_t height = -1 * (Y / 4), bottom = Y / 2, space = X / 50, lw = X / 13;
-    int64_t cx = X / 5;
-    // W
-    line(cx, bottom + height, cx, bottom);
-    line(cx, bottom, cx + lw / 2, bottom + height / 2);
-    cx += lw / 2;
-    line(cx, bottom + height / 2, cx + lw / 2, bottom);
-    cx += lw / 2;
-    line(cx, bottom + height, cx, bottom);
-    cx += space;
-    // e
-    auto letter_e = [&]() {
-        line(cx, bottom + height / 2, cx, bottom);
-        line(cx, bottom, cx + lw, bottom);
-        line(cx, bottom + height / 4, cx + lw, bottom + height / 4);
-        line(cx + lw, bottom + height / 2, cx + lw, bottom + height / 4);
-        line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
-        cx += lw + space;
-    };
-    letter_e();
-    // l
-    line(cx, bottom, cx, bottom + height);
-    cx += space;
-    // c
-    line(cx, bottom + height / 2, cx, bottom);
-    line(cx, bottom, cx + lw, bottom);
-    line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
-    cx += lw + space;
-    // o
-    line(cx, bottom + height / 2, cx, bottom);
-    line(cx, bottom, cx + lw, bottom);
-    line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
-    line(cx + lw, bottom + height / 2, cx + lw, bottom);
-    cx += lw + space;
-    // m
-    line(cx, bottom + height / 2, cx, bottom);
-    line(cx, bottom + height / 2, cx + lw, bottom + height / 2);
-    line(cx + lw, bottom + height / 2, cx + lw, bottom);
-    line(cx + lw / 2, bottom, cx + lw / 2, bottom + height / 2);
-    cx += lw + space;
-    // e
-    letter_e();
-    // !
-    line(cx, height / 10 + bottom, cx, bottom);
-    line(cx, height / 5 + bottom, cx, bottom + height);
-    if (!ok) return BLBM_EINVAL;  // Line::new(..).unwrap() would panic
+    for (size_t q = 0; q + 3 < v.size(); q += 4)
+        if (!line_points(Pt(v[q], v[q + 1]), Pt(v[q + 2], v[q + 3]), X, Y, false, &blob))
+            return BLBM_EINVAL;  // Line::new(..).unwrap() would panic
     return draw_set(h, blob, (uint64_t)X, 1);
 }
 

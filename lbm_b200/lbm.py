@@ -102,6 +102,7 @@ PROTOTYPES = {
     "blbm_timer_stop": (_I, [_P, C.POINTER(_F)]),
     "blbm_rasterize_line": (_I, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _I, _P, _SZ,
                                  C.POINTER(_SZ)]),
+    "blbm_preset_lines": (_I, [_I, C.c_int64, C.c_int64, _P, _SZ, C.POINTER(_SZ)]),
     "blbm_draw_line": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "blbm_erase_line": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "blbm_curl_barrier": (_I, [_P]),
@@ -446,6 +447,17 @@ def rasterize_line(p1, p2, xdim, ydim, erase=False):
     out = np.empty((n.value, 2), np.int64)
     L.blbm_rasterize_line(int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]), int(xdim), int(ydim), int(erase),
                           out.ctypes.data, n.value, C.byref(n))
+    return out
+
+
+def preset_lines(preset, xdim, ydim):
+    """End points of the thick lines of a barrier preset (0 curl, 1 chaos, 2 welcome; lbm.rs:1367-1480) as an (n, 4)
+    int64 array of (x1, y1, x2, y2), in the order the reference creates them."""
+    L = load_library()
+    n = _SZ()
+    _check(L.blbm_preset_lines(int(preset), int(xdim), int(ydim), None, 0, C.byref(n)))
+    out = np.empty((n.value, 4), np.int64)
+    _check(L.blbm_preset_lines(int(preset), int(xdim), int(ydim), out.ctypes.data, n.value, C.byref(n)))
     return out
 
 

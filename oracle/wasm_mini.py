@@ -323,9 +323,17 @@ class Instance:
         out = self._invoke(fidx, list(args))
         return out[0] if len(out) == 1 else (tuple(out) if out else None)
 
-    def _invoke(self, fidx, args):
+    def run_fragment(self, fidx, start_pc, locals_set):
+        """Execute function `fidx` from instruction index `start_pc` with the given locals ({index: value}, the rest
+        zero) until control leaves the enclosing blocks (a branch past the fragment's own labels, a return, or the end
+        of the body).  For code that rustc inlined into a large function — e.g. a `match` arm of an event loop — and
+        that cannot be called on its own: the caller supplies the locals the fragment reads."""
+        nparams = len(self.m.type_of(fidx)[0])
+        return self._invoke(fidx, [0] * nparams, start_pc=start_pc, locals_set=locals_set)
+
+    def _invoke(self, fidx, args, start_pc=0, locals_set=None):
         m = self.m
-        if fidx in self.hooks:
+        if fidx in self.hooks and not start_pc:
             r = self.hooks[fidx](self, *args)
             return [] if r is None else [r]
         if fidx < m.n_imports:
@@ -339,10 +347,12 @@ class Instance:
         params, results = m.type_of(fidx)
         local_types, code = m.decode(fidx)
         loc = args + [0.0 if t in (0x7D, 0x7C) else 0 for t in local_types]
+        for k, v in (locals_set or {}).items():
+            loc[k] = v
         st = []
         ctl = []  # (is_loop, continuation pc, stack height, arity)
         mem = self.mem
-        pc, n = 0, len(code)
+        pc, n = start_pc, len(code)
         pk, up = struct.pack_into, struct.unpack_from
         while pc < n:
             ins = code[pc]

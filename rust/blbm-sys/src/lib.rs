@@ -58,6 +58,7 @@ extern "C" {
     pub fn blbm_write_barrier_rows(h: *mut blbm_t, row_begin: u64, nrows: u64, mask: *const u8) -> c_int;
     pub fn blbm_rasterize_line(x1: i64, y1: i64, x2: i64, y2: i64, xdim: i64, ydim: i64, erase: c_int, xy: *mut i64,
                                capacity: usize, count: *mut usize) -> c_int;
+    pub fn blbm_preset_lines(preset: c_int, xdim: i64, ydim: i64, xyxy: *mut i64, capacity: usize, count: *mut usize) -> c_int;
     pub fn blbm_draw_line(h: *mut blbm_t, x1: i64, y1: i64, x2: i64, y2: i64) -> c_int;
     pub fn blbm_erase_line(h: *mut blbm_t, x1: i64, y1: i64, x2: i64, y2: i64) -> c_int;
     pub fn blbm_curl_barrier(h: *mut blbm_t) -> c_int;

@@ -18,6 +18,14 @@
     point sets of thick lines, with the un-vendored `line_drawing 1.0.0` Bresenham as compiled into the binary —
     row N2 (the rasteriser in front of draw_points).
 
+  * the barrier presets `LBM::curl_barrier`, `chaos_barrier`, `welcome_barrier` (lbm.rs:1367-1480).  rustc inlined them
+    into the event-loop closure (lib.rs:108-135, the `match *BARRIER_PRESET` arms), so they cannot be called; instead
+    the interpreter EXECUTES THE ARM ITSELF: `Instance.run_fragment` starts at the arm's first instruction with the
+    two locals it reads (`&mut lbm`, `&driver`) pointing at a fabricated LBM (xdim, ydim) and runs until control
+    leaves the arm, with `Line::new` logged (its six integer arguments: the end-point arithmetic) and
+    `LBM::draw_shape` served by the host (the `dyn Shape` it is handed is read out through its own vtable's
+    `get_points`): every thick line of every preset and the exact point sets drawn, in order -> wasm_presets.npz.
+
 The binary carries no name section, so the functions are addressed by index and each index is checked against a
 fingerprint (signature, floating-point constants, the "Endpoints (" format string it refers to, its callees) before
 it is trusted; the SHA-256 of the binary is stored with the results.  None of these functions touches an import on
@@ -48,6 +56,9 @@ SINGLE_CELL_SIZES = ((16, 12), (64, 32), (30, 17), (9, 7))
 # LBM::iterate against a mock of wgpu's `dyn DynContext`: vtable slots of this build, identified on draw_shape (whose
 # call sequence is known from lbm.rs:1341-1356) — and more LBM fields, found by perturbing them
 F_ITERATE = 246
+# the barrier presets are arms of a `match` inside the event-loop closure (the one function that calls Line::new
+# dozens of times); PRESET_SIZES are lattice sizes on which every end point is valid (Line::new(..).unwrap())
+PRESET_SIZES = ((512, 256), (300, 170), (1000, 500), (130, 64), (1920, 1080))
 SLOT = {"queue_write_buffer": 85, "queue_submit": 91, "device_create_command_encoder": 37, "begin_compute_pass": 72,
         "end_compute_pass": 73, "encoder_finish": 76, "set_pipeline": 96, "set_bind_group": 97,
         "dispatch_workgroups": 105}
@@ -372,8 +383,109 @@ class Reference:
         return self._read_set(inst, cur)
 
 
+class _Done(Exception):
+    pass
+
+
+def locate_presets(m):
+    """(function index, {name: (start pc, number of draw_shape calls)}, lbm local, driver local) of the three preset
+    arms, found by structure: the closure is the function with >= 30 calls of Line::new; its calls of draw_shape
+    split them into welcome (28 lines, one Blob drawn), curl (1 line, 1 draw) and chaos (4 lines, 4 draws); an arm
+    starts where its shadow-stack frame is opened (`global.get 0` right after the `end` of the previous arm)."""
+    cands = []
+    for k in range(len(m.bodies)):
+        f = k + m.n_imports
+        code = m.decode(f)[1]
+        n = sum(1 for i in code if i[0] == 0x10 and i[1] == F_LINE_NEW)
+        if n >= 30:
+            cands.append(f)
+    assert len(cands) == 1, cands
+    f = cands[0]
+    code = m.decode(f)[1]
+    lines = [pc for pc, i in enumerate(code) if i[0] == 0x10 and i[1] == F_LINE_NEW]
+    draws = [pc for pc, i in enumerate(code) if i[0] == 0x10 and i[1] == F_DRAW_SHAPE]
+    # arms in code order: 28 lines + 1 draw, 1 line + 1 draw, then (line, draw) x 4
+    assert all(a < draws[0] for a in lines[:28]) and lines[28] > draws[0]
+    assert draws[0] < lines[28] < draws[1] < lines[29] < draws[2] < lines[30] < draws[3] < lines[31] < draws[4] < lines[32] < draws[5]
+
+    def arm_start(first_line_pc):
+        pc = first_line_pc
+        while not (code[pc][0] == 0x23 and code[pc][1] == 0 and code[pc - 1][0] == 0x0B):
+            pc -= 1
+            assert first_line_pc - pc < 120
+        return pc
+
+    arms = {"welcome": (arm_start(lines[0]), 1), "curl": (arm_start(lines[28]), 1), "chaos": (arm_start(lines[29]), 4)}
+    # the locals: draw_shape(&mut lbm, &driver, &shape, vtable) — the first two arguments of the curl arm's call
+    pc = draws[1]
+    j = pc - 3
+    while not (code[j][0] == 0x20 and code[j + 1][0] == 0x20 and code[j + 2][0] == 0x20):  # lbm, driver, shape base
+        j -= 1
+        assert pc - j < 12
+    lbm_local, drv_local = code[j][1], code[j + 1][1]
+    s = arms["curl"][0]
+    assert any(i[0] == 0x28 and i[1] == LBM_X for i in code[s:s + 12]) and [code[s + 6][0], code[s + 6][1]] == [0x20, lbm_local]
+    return f, arms, lbm_local, drv_local
+
+
+def preset_trace(ref, name, xdim, ydim):
+    """Run one preset arm of the event-loop closure: returns (the (x1, y1, x2, y2, xdim, ydim) of every Line::new
+    call in order, the sorted (x, y, on) point list of every draw_shape call in order)."""
+    m = ref.m
+    f, arms, lbm_local, drv_local = locate_presets(m)
+    start, ndraws = arms[name]
+    lines, draws = [], []
+    s32 = lambda v: v - (1 << 32) if v >= 1 << 31 else v  # noqa: E731
+
+    def line_new(i, out, *a):
+        lines.append(tuple(s32(v) for v in a))
+        del i.hooks[F_LINE_NEW]
+        try:
+            i._invoke(F_LINE_NEW, [out, *a])
+        finally:
+            i.hooks[F_LINE_NEW] = line_new
+
+    def draw_shape(i, me_, drv_, shape, vt):
+        assert (me_, drv_) == (me, drv)
+        get_points = m.table[i.u32(vt + 12)]  # {drop, size, align, get_points}
+        draws.append(Reference._read_set(i, i._invoke(get_points, [shape])[0]))
+        if len(draws) == ndraws:
+            raise _Done
+
+    inst = Instance(m, imports=ref.stubs, hooks={F_LINE_NEW: line_new, F_DRAW_SHAPE: draw_shape})
+    malloc = m.exports["__wbindgen_malloc"][1]
+    me, drv = inst.call(malloc, 2048, 8), inst.call(malloc, 1024, 8)
+    for a, n in ((me, 2048), (drv, 1024)):
+        inst.mem[a:a + n] = bytes(n)
+    struct.pack_into("<II", inst.mem, me + LBM_X, xdim, ydim)
+    try:
+        inst.run_fragment(f, start, {lbm_local: me, drv_local: drv})
+    except _Done:
+        pass
+    assert len(draws) == ndraws and not inst.called
+    return lines, draws
+
+
+def presets_main(ref):
+    out = {"wasm_sha256": np.bytes_(ref.sha256), "sizes": np.array(PRESET_SIZES, np.int64)}
+    for x, y in PRESET_SIZES:
+        for name in ("curl", "chaos", "welcome"):
+            lines, draws = preset_trace(ref, name, x, y)
+            out[f"{name}/{x}x{y}/lines"] = np.array(lines, np.int64).reshape(-1, 6)
+            for k, d in enumerate(draws):
+                out[f"{name}/{x}x{y}/draw{k}"] = np.array(d, np.int32).reshape(-1, 3)
+            print(f"{name}_barrier on {x}x{y}: {len(lines)} lines, draws of {[len(d) for d in draws]} cells", flush=True)
+    path = os.path.join(HERE, "wasm_presets.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+
+
 def main():
     ref = Reference()
+    if "presets" in sys.argv[1:]:
+        presets_main(ref)
+        return
+    presets_main(ref)
     out = {"wasm_sha256": np.bytes_(ref.sha256), "inflows": np.array(INFLOWS, np.float32)}
     out["set_equil"] = np.stack([ref.set_equil(u) for u in INFLOWS])
     for x, y in SINGLE_CELL_SIZES:

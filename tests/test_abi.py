@@ -151,7 +151,7 @@ def test_every_entry_point_rejects_a_null_handle_without_crashing():
     getters = {"blbm_get_compute_num": 0, "blbm_get_frame_num": 0, "blbm_get_launch_count": 0,
                "blbm_get_device_bytes": 0, "blbm_get_lazy_barriers_active": 0, "blbm_group_size": 0}
     no_handle = {"blbm_last_error", "blbm_abi_version", "blbm_device_count", "blbm_create", "blbm_create_slab",
-                 "blbm_create_group", "blbm_rasterize_line"}
+                 "blbm_create_group", "blbm_rasterize_line", "blbm_preset_lines"}
     checked = 0
     for name, (res, args) in host.PROTOTYPES.items():
         if name in no_handle:

@@ -431,3 +431,92 @@ def test_cuda_draw_line_paints_the_reference_binarys_cells(golden):
         lbm.close()
         done += 1
     assert done >= 10
+
+
+# ---- the barrier presets, pinned to the `match *BARRIER_PRESET` arms of the binary's event loop ----------------------
+PRESETS = os.path.join(HERE, "golden", "wasm_presets.npz")
+PRESET_IDS = {"curl": 0, "chaos": 1, "welcome": 2}
+
+
+@pytest.fixture(scope="module")
+def presets():
+    return np.load(PRESETS)
+
+
+def _preset_draws(presets, name, x, y):
+    out, k = [], 0
+    while f"{name}/{x}x{y}/draw{k}" in presets:
+        out.append(presets[f"{name}/{x}x{y}/draw{k}"])
+        k += 1
+    return out
+
+
+def test_preset_end_points_equal_the_reference_binarys_line_new_calls(presets, golden):
+    """LBM::curl_barrier / chaos_barrier / welcome_barrier (lbm.rs:1367-1480) are inlined into the event-loop closure of
+    the shipped binary; the fixture holds what that code passed to Line::new when the arm itself was executed.  The
+    product's end-point arithmetic (blbm_preset_lines, pure host code) must reproduce every argument in order."""
+    from lbm_b200.lbm import preset_lines
+    assert bytes(presets["wasm_sha256"]) == bytes(golden["wasm_sha256"])
+    n = 0
+    for x, y in presets["sizes"]:
+        x, y = int(x), int(y)
+        for name, pid in PRESET_IDS.items():
+            want = presets[f"{name}/{x}x{y}/lines"]
+            assert (want[:, 4] == x).all() and (want[:, 5] == y).all()
+            np.testing.assert_array_equal(preset_lines(pid, x, y), want[:, :4], err_msg=f"{name} on {x}x{y}")
+            n += len(want)
+    assert n == 5 * (1 + 4 + 28)
+
+
+def test_preset_masks_equal_what_the_reference_binary_draws(presets):
+    """the point sets the binary hands to draw_shape, preset by preset (chaos: four separate draws; welcome: one
+    Blob), against the oracle-side restatement and against the product's rasteriser applied to its own end points"""
+    from lbm_b200.lbm import preset_lines, rasterize_line
+    for x, y in presets["sizes"]:
+        x, y = int(x), int(y)
+        for name, pid in PRESET_IDS.items():
+            draws = _preset_draws(presets, name, x, y)
+            assert all((d[:, 2] == 1).all() for d in draws)
+            want = {(int(a), int(b)) for d in draws for a, b, _ in d}
+            got = {(p[0], p[1]) for p in getattr(barrier_shapes, name + "_barrier")(x, y)}
+            assert got == want, f"oracle {name} on {x}x{y}"
+            mine = set()
+            per_line = []
+            for x1, y1, x2, y2 in preset_lines(pid, x, y):
+                pts = rasterize_line((x1, y1), (x2, y2), x, y)
+                per_line.append({(int(a), int(b)) for a, b in pts})
+                mine |= per_line[-1]
+            assert mine == want, f"product {name} on {x}x{y}"
+            if name == "chaos":  # drawn line by line
+                for d, pl in zip(draws, per_line):
+                    assert {(int(a), int(b)) for a, b, _ in d} == pl
+
+
+@needs_reference
+def test_preset_fixture_reruns_live(presets):
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_wasm_golden as gen
+    ref = gen.Reference()
+    assert ref.sha256.encode() == bytes(presets["wasm_sha256"])
+    for name in ("curl", "chaos"):
+        lines, draws = gen.preset_trace(ref, name, 300, 170)
+        np.testing.assert_array_equal(np.array(lines), presets[f"{name}/300x170/lines"])
+        for k, d in enumerate(draws):
+            np.testing.assert_array_equal(np.array(d, np.int32).reshape(-1, 3), presets[f"{name}/300x170/draw{k}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["curl", "chaos", "welcome"])
+def test_cuda_presets_paint_what_the_reference_binary_draws(presets, name):
+    from lbm_b200 import LBM
+    for x, y in ((300, 170), (512, 256), (1000, 500)):
+        lbm = LBM(1.25, x, y)
+        getattr(lbm, name + "_barrier")()
+        want = np.zeros((y, x), np.uint32)
+        want[0] = want[-1] = 1
+        for d in _preset_draws(presets, name, x, y):
+            want[d[:, 1], d[:, 0]] = d[:, 2]
+        np.testing.assert_array_equal(lbm.read_barrier(), want, err_msg=f"{name} on {x}x{y}")
+        lbm.iterate(3)  # and the lattice steps with it
+        lbm.close()
