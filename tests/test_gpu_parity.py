@@ -531,14 +531,28 @@ def test_api_fuzz_against_oracle(seed):
     _fuzz(lbm, ora, rng, w, h, f"fuzz seed {seed}", tunable=True)
 
 
-@pytest.mark.parametrize("seed", [21, 22, 23, 24, 25, 26, 27, 28])
+def _slab_fuzz_seeds():
+    import os
+    seeds = [21, 22, 23, 24, 25, 26, 27, 28]
+    extra = os.environ.get("BLBM_FUZZ_SLAB_SEEDS")  # a-b: soak range
+    if extra:
+        a, b = extra.split("-")
+        seeds += list(range(int(a), int(b) + 1))
+    return seeds
+
+
+@pytest.mark.parametrize("seed", _slab_fuzz_seeds())
 def test_api_fuzz_slab_group(seed):
-    """The same random walk over a lattice split into 2-4 linked slabs on cuda:0."""
+    """The same random walk over a lattice split into 2-4 linked slabs behind one group handle (on distinct GPUs
+    where the box has as many, else all on cuda:0)."""
     rng = np.random.default_rng(seed)
     w, h = int(rng.integers(40, 140)), int(rng.integers(16, 40))
     om = omega_from_viscosity(0.05)
     nslabs = int(rng.integers(2, 5))
-    grp = SlabGroup(om, w, h, devices=[0] * nslabs, kernel=Kernel(int(rng.integers(1, 3))),
+    from lbm_b200 import load_library
+    ndev = load_library().blbm_device_count()
+    devices = list(range(nslabs)) if ndev >= nslabs else [0] * nslabs
+    grp = SlabGroup(om, w, h, devices=devices, kernel=Kernel(int(rng.integers(1, 3))),
                     lazy_barriers=int(rng.integers(0, 3)))
     _fuzz(grp, Oracle(om, w, h), rng, w, h, f"slab fuzz seed {seed} x{nslabs}", tunable=False, nops=80)
 
