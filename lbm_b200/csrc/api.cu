@@ -396,8 +396,10 @@ int prime_step_graphs(blbm *h)
     return BLBM_OK;
 }
 
-// (re)capture the graphs if the kernel configuration changed since they were made
-int ensure_step_graphs(blbm *h)
+// Are the graphs usable for this call?  Captured at once the first time; after a change of configuration (omega,
+// kernel shape, chain table) only when the new configuration has been seen by two calls in a row, so that e.g. a
+// viscosity slider being dragged costs graph-less frames instead of a re-capture per frame.
+int ensure_step_graphs(blbm *h, bool *usable)
 {
     unsigned int omega_bits;
     memcpy(&omega_bits, &h->omega, sizeof(omega_bits));
@@ -407,11 +409,16 @@ int ensure_step_graphs(blbm *h)
             ((unsigned long long)(h->vec4_dense + 1) << 16) | ((unsigned long long)h->chain_active << 24) |
             ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)(h->vec4_index32 + 1) << 26),
         (unsigned long long)(uintptr_t)h->pool};
-    if (!h->graphs_primed || memcmp(h->graph_sig, sig, sizeof(sig)) != 0) {
-        const int rc = prime_step_graphs(h);
-        if (rc != BLBM_OK) return rc;
-        memcpy(h->graph_sig, sig, sizeof(sig));
+    *usable = true;
+    if (h->graphs_primed && memcmp(h->graph_sig, sig, sizeof(sig)) == 0) return BLBM_OK;
+    if (h->graphs_primed && memcmp(h->graph_pending_sig, sig, sizeof(sig)) != 0) {
+        memcpy(h->graph_pending_sig, sig, sizeof(sig));
+        *usable = false;
+        return BLBM_OK;
     }
+    const int rc = prime_step_graphs(h);
+    if (rc != BLBM_OK) return rc;
+    memcpy(h->graph_sig, sig, sizeof(sig));
     return BLBM_OK;
 }
 
@@ -429,6 +436,7 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
     uint32_t left = n;
     bool replayed = false;
     const bool graphs = graphs_wanted(h);
+    int graph_state = -1;  // decided once per call, after the chain table had its chance to change the configuration
     while (left) {
         const bool mom = left == 1 && store_moments;
         int rc;
@@ -445,8 +453,12 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
         // every step but the call's last (it may store moments) can go into a graph; the graphs are made (or re-made
         // after a change of omega / kernel shape / chain table) by the first call that could use one, however short,
         // so that the millisecond of capturing lands in a caller's warm-up and never in the middle of a frame loop
-        if (graphs && h->regimeT && (rc = ensure_step_graphs(h)) != BLBM_OK) return rc;
-        if (graphs && h->regimeT && !h->cls_pending && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
+        if (graphs && graph_state < 0) {
+            bool usable = false;
+            if ((rc = ensure_step_graphs(h, &usable)) != BLBM_OK) return rc;
+            graph_state = usable ? 1 : 0;
+        }
+        if (graph_state == 1 && h->regimeT && !h->cls_pending && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
             int q = 0;
             while (GRAPH_LEN[q] > left - 1) q++;
             if ((rc = run_step_graph(h, q)) != BLBM_OK) return rc;

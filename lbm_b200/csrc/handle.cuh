@@ -128,7 +128,7 @@ struct blbm_handle {
     // table change.
     static constexpr int GRAPH_SIZES = 4;  // 16, 8, 4, 2
     cudaGraphExec_t graph[2][2][GRAPH_SIZES] = {};  // [start parity][class buffer][length index]
-    unsigned long long graph_sig[4] = {0, 0, 0, 0};
+    unsigned long long graph_sig[4] = {0, 0, 0, 0}, graph_pending_sig[4] = {0, 0, 0, 0};
     bool graphs_primed = false;
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
     float *rgb = nullptr;  // colour buffer (rows x W x 3), allocated by the first blbm_color_map
