@@ -389,8 +389,9 @@ def state_digests(lbm, row_ranges):
 
 def multi_gpu_parity(job):
     """Before anything is timed: a verification lattice on the N linked slabs against the same lattice undivided
-    on rank 0's GPU — porous mask plus a cylinder straddling every slab boundary, 60 steps with a paint and an
-    erase across the boundaries mid-way — compared slab by slab through sha256 of all 18 populations, the moments
+    on rank 0's GPU — porous mask plus a cylinder straddling every slab boundary, 400 steps (slabs of 256 rows step in
+    ~50 us, so this is 400 back-to-back halo handshakes at the protocol's latency floor) with a paint and an erase
+    across the boundaries on the way — compared slab by slab through sha256 of all 18 populations, the moments
     and the curl output ("2-GPU vs 1-GPU bit-identical populations")."""
     from lbm_b200.lbm import slab_rows
     n = job.ngpu
@@ -405,11 +406,11 @@ def multi_gpu_parity(job):
     erase = np.stack([loc[::3], np.zeros_like(loc[::3])], 1)
 
     def run(lbm):
-        lbm.iterate(30)
+        lbm.iterate(150)
         lbm.draw_points(paint)
-        lbm.iterate(17)
+        lbm.iterate(137)
         lbm.draw_points(erase)
-        lbm.iterate(13)
+        lbm.iterate(113)
 
     lbm, r0, r1 = job.lattice(w, h, omega, u0, "porous", discs)
     run(lbm)
@@ -432,7 +433,7 @@ def multi_gpu_parity(job):
         flag = job.torch.tensor([1 if ok else 0], device="cuda")
         job.dist.broadcast(flag, 0)
         ok = bool(flag.item())
-    res = {"bit_identical": ok, "cells": w * h, "W": w, "H": h, "slabs": n, "steps": 60, "paints": 2,
+    res = {"bit_identical": ok, "cells": w * h, "W": w, "H": h, "slabs": n, "steps": 400, "paints": 2,
            "mask": "porous 15 % + one disc centred on every slab boundary",
            "compared": "sha256 of 18 populations + mx, my, rho + curl output per slab vs the undivided lattice on one GPU",
            "chain_table_active": bool(chain)}
