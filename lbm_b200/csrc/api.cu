@@ -486,11 +486,14 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
 
 // The mask changed in owned rows [lo, hi): bring the class words (and chunk flags) up to date.
 // big_change: the number of barrier cells may have changed enough for auto mode to decide afresh.
-int rebuild_class(blbm *h, uint32_t lo, uint32_t hi, bool big_change)
+// Decide which class buffer a rebuild of owned rows [lo, hi) goes to and which rows it must cover (see the comments
+// inside); returns false when there is nothing to rebuild.  Updates the handle's bookkeeping: the caller MUST launch.
+bool plan_class_rebuild(blbm *h, uint32_t lo, uint32_t hi, bool big_change, int *target_out, uint32_t *blo_out,
+                        uint32_t *bhi_out)
 {
     if (big_change) h->chain_declined = false;
     if (hi > h->rows) hi = h->rows;
-    if (lo >= hi) return BLBM_OK;
+    if (lo >= hi) return false;
     const bool had_diff = h->diff_hi > h->diff_lo;
     const uint32_t ulo = had_diff ? std::min(lo, h->diff_lo) : lo, uhi = had_diff ? std::max(hi, h->diff_hi) : hi;
     int target;
@@ -516,6 +519,17 @@ int rebuild_class(blbm *h, uint32_t lo, uint32_t hi, bool big_change)
         h->diff_lo = ulo;
         h->diff_hi = uhi;
     }
+    *target_out = target;
+    *blo_out = blo;
+    *bhi_out = bhi;
+    return true;
+}
+
+int rebuild_class(blbm *h, uint32_t lo, uint32_t hi, bool big_change)
+{
+    int target;
+    uint32_t blo, bhi;
+    if (!plan_class_rebuild(h, lo, hi, big_change, &target, &blo, &bhi)) return BLBM_OK;
     CK(launch_build_class(h->cls[target], h->mask, geom(h), h->chain_active ? h->cls[h->cls_cur] : nullptr,
                           h->rowflag[target], blo, bhi, h->stream));
     h->launches++;
@@ -1125,6 +1139,28 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         const int64_t ymax = (int64_t)(uniq[2 * (nu - 1)] / h->W) - (int64_t)h->row0;
         rlo = (uint32_t)std::max<int64_t>(0, ymin - 2);
         rhi = (uint32_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)h->rows, ymax + 3));
+    }
+    if (nu && nu <= SMALL_PAINT_PAIRS && !h->chain_active && h->rows * (uint64_t)h->W <= (4ull << 20)) {
+        // small lattice, small stroke, no chain table: one single-block launch does scatter + class rebuild with the
+        // pairs as kernel arguments (launch-bound regime: the general path's upload + two kernels cost 11 us)
+        const bool had_diff = h->diff_hi > h->diff_lo;
+        const uint32_t span_lo = (h->regimeT && !h->cls_pending && had_diff) ? std::min(rlo, h->diff_lo) : rlo;
+        const uint32_t span_hi = (h->regimeT && !h->cls_pending && had_diff) ? std::max(rhi, h->diff_hi) : rhi;
+        if (paint_small_fits(geom(h), (uint32_t)nu, span_lo, std::min(span_hi, h->rows))) {
+            int target;
+            uint32_t blo, bhi;
+            SmallPaint sp;
+            memcpy(sp.v, uniq.data(), nu * 2 * sizeof(uint64_t));
+            if (plan_class_rebuild(h, rlo, rhi, false, &target, &blo, &bhi)) {
+                CK(launch_paint_small(h->mask, h->cls[target], h->rowflag[target], geom(h), sp, (uint32_t)nu, blo, bhi,
+                                      h->stream));
+            } else {  // no owned row affected (the stroke lies in the mask halo only): scatter alone
+                CK(launch_paint_small(h->mask, h->cls[h->cls_cur], h->rowflag[h->cls_cur], geom(h), sp, (uint32_t)nu, 0, 0,
+                                      h->stream));
+            }
+            h->launches++;
+            return BLBM_OK;
+        }
     }
     if (nu) {
         if (h->d_pairs_cap < nu) {

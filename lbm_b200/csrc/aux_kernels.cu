@@ -118,6 +118,47 @@ __device__ __forceinline__ uint32_t mask_at(const uint8_t *mask, const SlabGeom 
 // One warp per 128-cell chunk of a row (4 cells per lane); PUBLIC selects the word of blbm_read_cell_class
 // (densely packed rows x W) instead of the kernel-facing word (plane layout) and skips the chunk flags.
 template <bool PUBLIC>
+__device__ __forceinline__ void build_class_chunk(uint16_t *cls, const uint8_t *mask, const SlabGeom &g,
+                                                  const uint16_t *keep_chain, uint8_t *rowflag, const uint32_t r,
+                                                  const uint32_t chunk, const uint32_t nchunk, const uint32_t lane)
+{
+    const int64_t gy = (int64_t)g.row0 + r;
+    uint32_t any = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t x = chunk * CHUNK + lane * 4u + q;
+        if (x >= g.P) continue;
+        uint16_t c = 0;
+        if (x < g.W) {
+            const bool bar = mask[mask_row_off(r, g.P) + x] == 1;
+            const bool skip = bar || x == 0 || gy >= (int64_t)g.Hg - 1;
+            uint32_t up = 0;
+#pragma unroll
+            for (int d = 0; d < 8; d++)
+                if (mask_at(mask, g, (int64_t)x - dir_dx(d), gy - dir_dy(d)) == 1) up |= 1u << d;
+            if (PUBLIC) {
+                c = (uint16_t)((bar ? PUB_BARRIER : 0) | (skip ? PUB_SKIP : 0) | (up << 2));
+            } else {
+                c = (uint16_t)((bar ? CLS_BARRIER : 0) | (skip ? CLS_SKIP : (uint16_t)up));
+                // cells whose state lives in the chain table stay there (a paint evicts the cells it
+                // touches before the mask changes, so a kept bit belongs to a cell that is still a barrier)
+                if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & (CLS_CHAIN | CLS_SLOT);
+            }
+        }
+        if (PUBLIC) {
+            if (x < g.W) cls[(size_t)r * g.W + x] = c;
+        } else {
+            cls[row_off(r, g.P) + x] = c;
+            any |= c;
+        }
+    }
+    if (!PUBLIC && rowflag) {
+        any = __reduce_or_sync(0xffffffffu, any);
+        if (lane == 0) rowflag[(size_t)r * nchunk + chunk] = any ? 1 : 0;
+    }
+}
+
+template <bool PUBLIC>
 __global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const SlabGeom g, const uint16_t *keep_chain,
                                    uint8_t *rowflag, const uint32_t row_begin, const uint32_t row_end)
 {
@@ -125,44 +166,45 @@ __global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const Sla
     const size_t nwarps_total = (size_t)(row_end - row_begin) * nchunk;
     const uint32_t lane = threadIdx.x & 31u;
     for (size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nwarps_total;
-         wid += ((size_t)gridDim.x * blockDim.x) >> 5) {
-        const uint32_t r = row_begin + (uint32_t)(wid / nchunk);
-        const uint32_t chunk = (uint32_t)(wid % nchunk);
-        const int64_t gy = (int64_t)g.row0 + r;
-        uint32_t any = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t x = chunk * CHUNK + lane * 4u + q;
-            if (x >= g.P) continue;
-            uint16_t c = 0;
-            if (x < g.W) {
-                const bool bar = mask[mask_row_off(r, g.P) + x] == 1;
-                const bool skip = bar || x == 0 || gy >= (int64_t)g.Hg - 1;
-                uint32_t up = 0;
-#pragma unroll
-                for (int d = 0; d < 8; d++)
-                    if (mask_at(mask, g, (int64_t)x - dir_dx(d), gy - dir_dy(d)) == 1) up |= 1u << d;
-                if (PUBLIC) {
-                    c = (uint16_t)((bar ? PUB_BARRIER : 0) | (skip ? PUB_SKIP : 0) | (up << 2));
-                } else {
-                    c = (uint16_t)((bar ? CLS_BARRIER : 0) | (skip ? CLS_SKIP : (uint16_t)up));
-                    // cells whose state lives in the chain table stay there (a paint evicts the cells it
-                    // touches before the mask changes, so a kept bit belongs to a cell that is still a barrier)
-                    if (keep_chain) c |= keep_chain[row_off(r, g.P) + x] & (CLS_CHAIN | CLS_SLOT);
-                }
-            }
-            if (PUBLIC) {
-                if (x < g.W) cls[(size_t)r * g.W + x] = c;
-            } else {
-                cls[row_off(r, g.P) + x] = c;
-                any |= c;
-            }
-        }
-        if (!PUBLIC && rowflag) {
-            any = __reduce_or_sync(0xffffffffu, any);
-            if (lane == 0) rowflag[(size_t)r * nchunk + chunk] = any ? 1 : 0;
-        }
+         wid += ((size_t)gridDim.x * blockDim.x) >> 5)
+        build_class_chunk<PUBLIC>(cls, mask, g, keep_chain, rowflag, row_begin + (uint32_t)(wid / nchunk),
+                                  (uint32_t)(wid % nchunk), nchunk, lane);
+}
+
+// A small paint on a small region in ONE launch of ONE block, the (location, value) pairs passed as kernel arguments:
+// scatter into the mask, block barrier, rebuild the class words of the affected rows.  Small lattices are
+// launch-bound — a 15-step frame of the 512 x 256 cylinder is 60 us — and the three operations of the general path
+// (upload, scatter kernel, class kernel) cost 11 us of it.
+__global__ void __launch_bounds__(1024) paint_small_kernel(uint8_t *mask, uint16_t *cls, uint8_t *rowflag, const SlabGeom g,
+                                                           const SmallPaint pairs, const uint32_t npairs,
+                                                           const uint32_t row_begin, const uint32_t row_end)
+{
+    if (threadIdx.x < npairs) {
+        const uint64_t loc = pairs.v[2 * threadIdx.x], val = pairs.v[2 * threadIdx.x + 1];
+        const uint64_t gy = loc / g.W;
+        const int64_t lr = (int64_t)gy - (int64_t)g.row0;
+        if (gy < g.Hg && lr >= -2 && lr < (int64_t)g.rows + 2)
+            mask[mask_row_off(lr, g.P) + (uint32_t)(loc - gy * g.W)] = (val == 1u) ? 1 : 0;
     }
+    __syncthreads();  // one block: every scatter store is visible to the class rebuild below
+    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
+    const uint32_t nwarps_total = (row_end - row_begin) * nchunk;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t wid = threadIdx.x >> 5; wid < nwarps_total; wid += blockDim.x >> 5)
+        build_class_chunk<false>(cls, mask, g, nullptr, rowflag, row_begin + wid / nchunk, wid % nchunk, nchunk, lane);
+}
+
+cudaError_t launch_paint_small(uint8_t *mask, uint16_t *cls, uint8_t *rowflag, const SlabGeom &g, const SmallPaint &pairs,
+                               uint32_t npairs, uint32_t row_begin, uint32_t row_end, cudaStream_t st)
+{
+    paint_small_kernel<<<1, 1024, 0, st>>>(mask, cls, rowflag, g, pairs, npairs, row_begin, row_end);
+    return cudaGetLastError();
+}
+
+bool paint_small_fits(const SlabGeom &g, uint32_t npairs, uint32_t row_begin, uint32_t row_end)
+{
+    const uint64_t chunks = (uint64_t)(row_end - row_begin) * ((g.P + CHUNK - 1) / CHUNK);
+    return npairs <= SMALL_PAINT_PAIRS && chunks <= 256;  // <= 8 chunk rows per warp of the block
 }
 
 static unsigned class_grid(const SlabGeom &g, uint32_t nrows)
@@ -938,6 +980,7 @@ cudaError_t preload_aux_kernels()
     BLBM_TOUCH(mask_scatter_kernel);
     BLBM_TOUCH(build_class_kernel<false>);
     BLBM_TOUCH(build_class_kernel<true>);
+    BLBM_TOUCH(paint_small_kernel);
     BLBM_TOUCH(precollision_moments_kernel);
     BLBM_TOUCH(curl_vec4_kernel);
     BLBM_TOUCH(summary_kernel<0>);
