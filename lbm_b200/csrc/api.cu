@@ -1140,27 +1140,13 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         rlo = (uint32_t)std::max<int64_t>(0, ymin - 2);
         rhi = (uint32_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)h->rows, ymax + 3));
     }
-    if (nu && nu <= SMALL_PAINT_PAIRS && !h->chain_active && h->rows * (uint64_t)h->W <= (4ull << 20)) {
-        // small lattice, small stroke, no chain table: one single-block launch does scatter + class rebuild with the
-        // pairs as kernel arguments (launch-bound regime: the general path's upload + two kernels cost 11 us)
-        const bool had_diff = h->diff_hi > h->diff_lo;
-        const uint32_t span_lo = (h->regimeT && !h->cls_pending && had_diff) ? std::min(rlo, h->diff_lo) : rlo;
-        const uint32_t span_hi = (h->regimeT && !h->cls_pending && had_diff) ? std::max(rhi, h->diff_hi) : rhi;
-        if (paint_small_fits(geom(h), (uint32_t)nu, span_lo, std::min(span_hi, h->rows))) {
-            int target;
-            uint32_t blo, bhi;
-            SmallPaint sp;
-            memcpy(sp.v, uniq.data(), nu * 2 * sizeof(uint64_t));
-            if (plan_class_rebuild(h, rlo, rhi, false, &target, &blo, &bhi)) {
-                CK(launch_paint_small(h->mask, h->cls[target], h->rowflag[target], geom(h), sp, (uint32_t)nu, blo, bhi,
-                                      h->stream));
-            } else {  // no owned row affected (the stroke lies in the mask halo only): scatter alone
-                CK(launch_paint_small(h->mask, h->cls[h->cls_cur], h->rowflag[h->cls_cur], geom(h), sp, (uint32_t)nu, 0, 0,
-                                      h->stream));
-            }
-            h->launches++;
-            return BLBM_OK;
-        }
+    if (nu && nu <= SMALL_PAINT_PAIRS && !h->chain_active) {
+        // small stroke, no chain table to evict from: the pairs go as kernel arguments, no upload
+        SmallPaint sp;
+        memcpy(sp.v, uniq.data(), nu * 2 * sizeof(uint64_t));
+        CK(launch_mask_scatter_args(h->mask, geom(h), sp, (uint32_t)nu, h->stream));
+        h->launches++;
+        return rebuild_class(h, rlo, rhi, false);
     }
     if (nu) {
         if (h->d_pairs_cap < nu) {

@@ -171,40 +171,27 @@ __global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const Sla
                                   (uint32_t)(wid % nchunk), nchunk, lane);
 }
 
-// A small paint on a small region in ONE launch of ONE block, the (location, value) pairs passed as kernel arguments:
-// scatter into the mask, block barrier, rebuild the class words of the affected rows.  Small lattices are
-// launch-bound — a 15-step frame of the 512 x 256 cylinder is 60 us — and the three operations of the general path
-// (upload, scatter kernel, class kernel) cost 11 us of it.
-__global__ void __launch_bounds__(1024) paint_small_kernel(uint8_t *mask, uint16_t *cls, uint8_t *rowflag, const SlabGeom g,
-                                                           const SmallPaint pairs, const uint32_t npairs,
-                                                           const uint32_t row_begin, const uint32_t row_end)
+// A small paint: the (location, value) pairs travel as kernel arguments, which saves the upload of the general path
+// (small lattices are launch-bound: a 15-step frame of the 512 x 256 cylinder is 60 us, the upload 3 us of it).
+// (Fusing the class rebuild into the same single-block launch was measured and rejected: one SM rebuilding 13 rows
+// takes longer than a second launch spread over the chip, 14.4 vs 11.4 us per paint.)
+__global__ void mask_scatter_args_kernel(uint8_t *mask, const SlabGeom g, const SmallPaint pairs, const uint32_t npairs)
 {
-    if (threadIdx.x < npairs) {
-        const uint64_t loc = pairs.v[2 * threadIdx.x], val = pairs.v[2 * threadIdx.x + 1];
-        const uint64_t gy = loc / g.W;
-        const int64_t lr = (int64_t)gy - (int64_t)g.row0;
-        if (gy < g.Hg && lr >= -2 && lr < (int64_t)g.rows + 2)
-            mask[mask_row_off(lr, g.P) + (uint32_t)(loc - gy * g.W)] = (val == 1u) ? 1 : 0;
-    }
-    __syncthreads();  // one block: every scatter store is visible to the class rebuild below
-    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
-    const uint32_t nwarps_total = (row_end - row_begin) * nchunk;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t wid = threadIdx.x >> 5; wid < nwarps_total; wid += blockDim.x >> 5)
-        build_class_chunk<false>(cls, mask, g, nullptr, rowflag, row_begin + wid / nchunk, wid % nchunk, nchunk, lane);
+    if (threadIdx.x >= npairs) return;
+    const uint64_t loc = pairs.v[2 * threadIdx.x], val = pairs.v[2 * threadIdx.x + 1];
+    const uint64_t gy = loc / g.W;
+    const int64_t lr = (int64_t)gy - (int64_t)g.row0;
+    if (gy < g.Hg && lr >= -2 && lr < (int64_t)g.rows + 2)
+        mask[mask_row_off(lr, g.P) + (uint32_t)(loc - gy * g.W)] = (val == 1u) ? 1 : 0;
 }
 
-cudaError_t launch_paint_small(uint8_t *mask, uint16_t *cls, uint8_t *rowflag, const SlabGeom &g, const SmallPaint &pairs,
-                               uint32_t npairs, uint32_t row_begin, uint32_t row_end, cudaStream_t st)
+cudaError_t launch_mask_scatter_args(uint8_t *mask, const SlabGeom &g, const SmallPaint &pairs, uint32_t npairs,
+                                     cudaStream_t st)
 {
-    paint_small_kernel<<<1, 1024, 0, st>>>(mask, cls, rowflag, g, pairs, npairs, row_begin, row_end);
+    if (npairs == 0) return cudaSuccess;
+    if (npairs > SMALL_PAINT_PAIRS) return cudaErrorInvalidValue;
+    mask_scatter_args_kernel<<<1, SMALL_PAINT_PAIRS, 0, st>>>(mask, g, pairs, npairs);
     return cudaGetLastError();
-}
-
-bool paint_small_fits(const SlabGeom &g, uint32_t npairs, uint32_t row_begin, uint32_t row_end)
-{
-    const uint64_t chunks = (uint64_t)(row_end - row_begin) * ((g.P + CHUNK - 1) / CHUNK);
-    return npairs <= SMALL_PAINT_PAIRS && chunks <= 256;  // <= 8 chunk rows per warp of the block
 }
 
 static unsigned class_grid(const SlabGeom &g, uint32_t nrows)
@@ -980,7 +967,7 @@ cudaError_t preload_aux_kernels()
     BLBM_TOUCH(mask_scatter_kernel);
     BLBM_TOUCH(build_class_kernel<false>);
     BLBM_TOUCH(build_class_kernel<true>);
-    BLBM_TOUCH(paint_small_kernel);
+    BLBM_TOUCH(mask_scatter_args_kernel);
     BLBM_TOUCH(precollision_moments_kernel);
     BLBM_TOUCH(curl_vec4_kernel);
     BLBM_TOUCH(summary_kernel<0>);

@@ -370,15 +370,13 @@ cudaError_t launch_mask_scatter(uint8_t *mask, const SlabGeom &g, const uint64_t
 // Only owned rows [row_begin, row_end) are rebuilt (a paint touches a few rows).
 cudaError_t launch_build_class(uint16_t *cls, const uint8_t *mask, const SlabGeom &g, const uint16_t *keep_chain,
                                uint8_t *rowflag, uint32_t row_begin, uint32_t row_end, cudaStream_t st);
-// a paint of at most SMALL_PAINT_PAIRS cells whose class rebuild covers at most 256 row chunks: scatter + rebuild in
-// one single-block launch, the pairs travelling as kernel arguments (no chain table: the caller evicts separately)
+// a paint of at most SMALL_PAINT_PAIRS cells: the pairs travel as kernel arguments instead of through an upload
 constexpr uint32_t SMALL_PAINT_PAIRS = 64;
 struct SmallPaint {
     uint64_t v[2 * SMALL_PAINT_PAIRS];
 };
-bool paint_small_fits(const SlabGeom &g, uint32_t npairs, uint32_t row_begin, uint32_t row_end);
-cudaError_t launch_paint_small(uint8_t *mask, uint16_t *cls, uint8_t *rowflag, const SlabGeom &g, const SmallPaint &pairs,
-                               uint32_t npairs, uint32_t row_begin, uint32_t row_end, cudaStream_t st);
+cudaError_t launch_mask_scatter_args(uint8_t *mask, const SlabGeom &g, const SmallPaint &pairs, uint32_t npairs,
+                                     cudaStream_t st);
 // the public class words of blbm_read_cell_class, densely packed rows x W
 cudaError_t launch_build_public_class(uint16_t *dst, const uint8_t *mask, const SlabGeom &g, cudaStream_t st);
 cudaError_t launch_precollision_moments(const float *const *f8, float *mx, float *my, float *rho, uint32_t W,
