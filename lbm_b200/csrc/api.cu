@@ -343,11 +343,12 @@ void drop_step_graphs(blbm *h)
 {
     for (auto &par : h->graph)
         for (auto &cls : par)
-            for (cudaGraphExec_t &g : cls)
-                if (g) {
-                    cudaGraphExecDestroy(g);
-                    g = nullptr;
-                }
+            for (auto &pend : cls)
+                for (cudaGraphExec_t &g : pend)
+                    if (g) {
+                        cudaGraphExecDestroy(g);
+                        g = nullptr;
+                    }
     h->graphs_primed = false;
 }
 
@@ -360,6 +361,7 @@ int prime_step_graphs(blbm *h)
     int rc = BLBM_OK;
     for (int par = 0; par < 2 && rc == BLBM_OK; par++)
         for (int cls = 0; cls < 2 && rc == BLBM_OK; cls++)
+          for (int pend = 0; pend < 2 && rc == BLBM_OK; pend++)
             for (int q = 0; q < blbm::GRAPH_SIZES && rc == BLBM_OK; q++) {
                 cudaGraph_t graph = nullptr;
                 cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
@@ -373,13 +375,14 @@ int prime_step_graphs(blbm *h)
                     const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
                     rc = launch_step(h, MODE_FUSED, x, y, false);
                     h->step++;
+                    if (pend && k == 0) h->cls_cur ^= 1;  // the pending stream saw the old classification; swap
                 }
                 e = cudaStreamEndCapture(h->stream, &graph);
                 if (rc == BLBM_OK && e != cudaSuccess) rc = fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
                 if (rc == BLBM_OK) {
-                    e = cudaGraphInstantiate(&h->graph[par][cls][q], graph, 0);
+                    e = cudaGraphInstantiate(&h->graph[par][cls][pend][q], graph, 0);
                     if (e != cudaSuccess) {
-                        h->graph[par][cls][q] = nullptr;
+                        h->graph[par][cls][pend][q] = nullptr;
                         rc = fail(BLBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
                     }
                 }
@@ -425,9 +428,10 @@ int ensure_step_graphs(blbm *h, bool *usable)
 // GRAPH_LEN[q] fused, non-moment-storing steps starting at the current parity, as one graph launch
 int run_step_graph(blbm *h, int q)
 {
-    CK(cudaGraphLaunch(h->graph[h->step % 2][h->cls_cur][q], h->stream));
+    CK(cudaGraphLaunch(h->graph[h->step % 2][h->cls_cur][h->cls_pending ? 1 : 0][q], h->stream));
     h->step += GRAPH_LEN[q];
     h->launches += GRAPH_LEN[q];
+    consume_pending_class(h);  // (its first step ran on the old class buffer)
     return BLBM_OK;
 }
 
@@ -458,7 +462,7 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
             if ((rc = ensure_step_graphs(h, &usable)) != BLBM_OK) return rc;
             graph_state = usable ? 1 : 0;
         }
-        if (graph_state == 1 && h->regimeT && !h->cls_pending && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
+        if (graph_state == 1 && h->regimeT && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
             int q = 0;
             while (GRAPH_LEN[q] > left - 1) q++;
             if ((rc = run_step_graph(h, q)) != BLBM_OK) return rc;

@@ -122,12 +122,12 @@ struct blbm_handle {
     unsigned long long *chain_counter = nullptr;
     unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
     // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): runs of 16, 8, 4 and 2 fused,
-    // non-moment-storing steps are captured into CUDA graphs — all four lengths for both start parities and both
-    // class buffers at once, the first time a run is wanted (about a millisecond, in the caller's first iterate), so
-    // that no capture ever lands inside a frame loop — and re-captured when omega, the kernel shape or the chain
-    // table change.
+    // non-moment-storing steps are captured into CUDA graphs — all four lengths for both start parities, both
+    // class buffers, and with / without a class swap pending after the first step (the step after a paint) at once,
+    // the first time a run is wanted (a couple of milliseconds, in the caller's first iterate), so that no capture
+    // ever lands inside a frame loop — and re-captured when omega, the kernel shape or the chain table change.
     static constexpr int GRAPH_SIZES = 4;  // 16, 8, 4, 2
-    cudaGraphExec_t graph[2][2][GRAPH_SIZES] = {};  // [start parity][class buffer][length index]
+    cudaGraphExec_t graph[2][2][2][GRAPH_SIZES] = {};  // [start parity][class buffer][swap pending][length index]
     unsigned long long graph_sig[4] = {0, 0, 0, 0}, graph_pending_sig[4] = {0, 0, 0, 0};
     bool graphs_primed = false;
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
