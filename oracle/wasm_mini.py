@@ -303,6 +303,7 @@ class Instance:
         self.steps = 0
         self.max_steps = max_steps
         self.called = []
+        self.stack_trace = []
 
     # -- memory helpers for the host side
     def read(self, addr, n):
@@ -346,6 +347,18 @@ class Instance:
             return [] if r is None else [r]
         params, results = m.type_of(fidx)
         local_types, code = m.decode(fidx)
+        self.stack_trace.append(fidx)
+        try:
+            return self._run(fidx, args, start_pc, locals_set, results, local_types, code)
+        except Trap as e:
+            if not hasattr(e, "stack"):
+                e.stack = list(self.stack_trace)  # function indices, outermost first: where the trap happened
+            raise
+        finally:
+            self.stack_trace.pop()
+
+    def _run(self, fidx, args, start_pc, locals_set, results, local_types, code):
+        m = self.m
         loc = args + [0.0 if t in (0x7D, 0x7C) else 0 for t in local_types]
         for k, v in (locals_set or {}).items():
             loc[k] = v
@@ -446,7 +459,7 @@ class Instance:
                         st.append(r)
                     continue
                 if i >= len(m.table) or m.table[i] is None:
-                    raise Trap("undefined table element")
+                    raise Trap(f"undefined table element {i:#x} (call_indirect at pc {pc - 1} of function {fidx})")
                 f = m.table[i]
                 if m.type_of(f) != m.types[ins[1]]:
                     raise Trap("indirect call type mismatch")

@@ -466,6 +466,204 @@ def preset_trace(ref, name, xdim, ydim):
     return lines, draws
 
 
+def locate_lbm_new(m):
+    """`LBM::new` (lbm.rs:726-1049) is inlined into the async start-up closure (`run_wasm`, the one other function
+    besides the event loop that calls set_equil with the constant 0.1 in front).  Its wgpu object creations are NOT
+    inlined: nine calls of Device::create_bind_group_layout, then set_equil, create_buffer_init (the callee with
+    several context calls), create_bind_group, create_pipeline_layout, create_shader_module, create_compute_pipeline,
+    create_render_pipeline — told apart by how often the closure (or its helpers) call them.  Returns the closure,
+    the pc where LBM::new starts (x and y are read from the future's state), the creation functions and the Drop
+    impls of wgpu objects (one-argument functions that call the context once)."""
+    start_f = [k + m.n_imports for k in range(len(m.bodies))
+               if any(i[0] == 0x10 and i[1] == F_SET_EQUIL and j and m.decode(k + m.n_imports)[1][j - 3][0] == 0x43
+                      for j, i in enumerate(m.decode(k + m.n_imports)[1]))]
+    start_f = [f for f in start_f if len(m.decode(f)[1]) > 5000 and sum(1 for i in m.decode(f)[1] if i[0] == 0x11) > 20]
+    assert len(start_f) == 1, start_f
+    f = start_f[0]
+    code = m.decode(f)[1]
+    eq = next(pc for pc, i in enumerate(code) if i[0] == 0x10 and i[1] == F_SET_EQUIL)
+
+    def one_ctx_call(fn):
+        c = m.decode(fn)[1]
+        return fn >= m.n_imports and m.type_of(fn) == ([I32] * 3, []) and sum(1 for i in c if i[0] == 0x11) == 1
+
+    import collections
+    before = collections.Counter(i[1] for i in code[:eq] if i[0] == 0x10 and one_ctx_call(i[1]))
+    (bgl, nb), = [(k, v) for k, v in before.items() if v == 9]
+    # LBM::new ends with the render pipeline, ~3300 instructions after set_equil (the closure goes on to build the
+    # event loop, which creates more objects)
+    after = collections.Counter(i[1] for i in code[eq:eq + 3300] if i[0] == 0x10 and one_ctx_call(i[1]))
+    by_count = {v: k for k, v in after.items()}
+    assert sorted(after.values()) == [1, 6, 8, 16, 17], after  # render pipeline, layouts, bind groups, pipelines, shaders
+    buf_init = [k for k in {i[1] for i in code[eq:eq + 800] if i[0] == 0x10 and i[1] >= m.n_imports}
+                if sum(1 for j in m.decode(k)[1] if j[0] == 0x11) >= 5]
+    assert len(buf_init) == 1
+    drops = [k + m.n_imports for k in range(len(m.bodies))
+             if m.type_of(k + m.n_imports) == ([I32], []) and len(m.decode(k + m.n_imports)[1]) < 60
+             and sum(1 for i in m.decode(k + m.n_imports)[1] if i[0] == 0x11) == 1]
+    first = next(pc for pc, i in enumerate(code) if i[0] == 0x10 and i[1] == bgl)
+    pc = first
+    while not (code[pc][0] == 0x23 and code[pc][1] == 0):  # the frame of LBM::new is opened with `global.get 0`
+        pc -= 1
+        assert first - pc < 80
+    start = pc - 6  # local.get 0; i32.load w; local.set; local.get 0; i32.load h; local.set
+    assert [code[start][0], code[start + 1][0], code[start + 3][0], code[start + 4][0]] == [0x20, 0x28, 0x20, 0x28]
+    assert code[start + 4][1] == code[start + 1][1] + 4
+    # the Driver sits at a fixed offset of the closure's own frame: `&driver.device` = frame + k + DRIVER_DEVICE
+    return {"f": f, "start": start, "state_x": code[start + 1][1], "state_local": code[start][1],
+            "bgl": bgl, "bg": by_count[8], "pl": by_count[6], "shader": by_count[17], "cpipe": by_count[16],
+            "rpipe": by_count[1], "buffer_init": buf_init[0], "drops": drops}
+
+
+def bindgroup_trace(ref, x=12, y=7):
+    """Run LBM::new inside the start-up closure of the binary (fragment execution from where it reads x and y) with
+    the wgpu object creations served by the host: every returned object is filled with a pointer to a tag (which
+    doubles as a harmless ArcInner / Box vtable), so that it can be recognised wherever the code stores or passes it.
+    Returns what the binary itself did: the buffers it created (order, contents, usage), the entries of every bind
+    group (binding -> buffer), where each buffer of `data_buffers[b][k]` and each bind group ends up in the assembled
+    `LBM` value (field offsets — the very offsets `LBM::iterate` passes to set_bind_group, see iterate_trace)."""
+    m = ref.m
+    loc = locate_lbm_new(m)
+    inst = Instance(m, imports=ref.stubs, max_steps=400_000_000)
+    malloc = m.exports["__wbindgen_malloc"][1]
+    virt, nslot, RC = 1 << 20, 256, 0x40000000
+    uni = inst.call(malloc, 4 * nslot, 8)  # as in _mock_wgpu: the context's ArcInner and vtable in one object
+    struct.pack_into("<III", inst.mem, uni, virt, 0, 8)
+    for k in range(3, nslot):
+        struct.pack_into("<I", inst.mem, uni + 4 * k, virt + k)
+    anyvt = inst.call(malloc, 16, 4)
+    struct.pack_into("<IIII", inst.mem, anyvt, virt + 250, 0, 1, virt + 251)
+    state, frame, arena = inst.call(malloc, 8192, 8), inst.call(malloc, 8192, 8), inst.call(malloc, 64 * 512, 8)
+    for a, n in ((state, 8192), (frame, 8192), (arena, 64 * 512)):
+        inst.mem[a:a + n] = bytes(n)
+    for off in range(16, 2048, 4):
+        struct.pack_into("<I", inst.mem, frame + off, uni)  # every word of the Driver -> the mock context
+    struct.pack_into("<II", inst.mem, state + loc["state_x"], x, y)
+    tags, buffers, groups, layouts, created = {}, [], [], [], []
+
+    def new_tag(kind, n):
+        t = arena + 64 * len(tags)
+        tags[t] = (kind, n)
+        inst.write_u32(t, RC)  # a strong count that never reaches zero / a vtable whose drop is the no-op below
+        return t
+
+    def fill(ret, nbytes, t):
+        for o in range(0, nbytes, 4):
+            inst.write_u32(ret + o, t)
+
+    def buffer_of(ptr):
+        """which buffer a `&wgpu::Buffer` points at: a tag in its first word (create_buffer_init, served whole) or
+        the ObjectId the mock context handed out (Device::create_buffer is inlined; &buffer.id is 48 bytes in)"""
+        t = inst.u32(ptr)
+        if t in tags and tags[t][0] == "buffer":
+            return tags[t][1]
+        oid = inst.u32(ptr + 48)
+        return next(b["index"] for b in buffers if b.get("object_id") == oid)
+
+    def create_buffer_init(i, ret, dev, desc):  # BufferInitDescriptor { label, contents: &[u8], usage }
+        lp, ll, cp, cl, usage = (i.u32(desc + 4 * k) for k in range(5))
+        data = i.read(cp, cl)
+        w = np.frombuffer(data[:cl // 4 * 4], np.uint32)
+        buffers.append({"index": len(buffers), "how": "create_buffer_init", "label": i.read(lp, ll).decode() if lp else None,
+                        "bytes": cl, "usage": usage, "first_word": int(w[0]) if len(w) else None,
+                        "uniform_contents": bool(len(w) and (w == w[0]).all()),
+                        "sha256": hashlib.sha256(data).hexdigest()})
+        fill(ret, SIZEOF_BUFFER, new_tag("buffer", len(buffers) - 1))
+
+    def create_bind_group(i, ret, dev, desc):  # BindGroupDescriptor { label, entries: &[BindGroupEntry], layout }
+        ep, en, lay = i.u32(desc + 8), i.u32(desc + 12), i.u32(desc + 16)
+        entries = []
+        for k in range(en):  # BindGroupEntry (40 bytes): the &Buffer of BufferBinding at +24, `binding` at +32
+            e = ep + 40 * k
+            entries.append([i.u32(e + 32), buffer_of(i.u32(e + 24))])
+        groups.append({"index": len(groups), "layout": tags[i.u32(lay)][1], "entries": entries})
+        fill(ret, 24, new_tag("bind_group", len(groups) - 1))
+
+    def creator(kind):
+        def h(i, ret, dev, desc):
+            n = sum(1 for c in created if c == kind)
+            created.append(kind)
+            fill(ret, 24, new_tag(kind, n))
+        return h
+
+    class LbmAssembled(Exception):
+        pass
+
+    oid, create_slot, other_slots = [1000], [None], []
+
+    def method(k):
+        def h(i, *a):
+            if k in (250, 251):
+                return None
+            if len(groups) == 16 and i.u32(frame + lbm_base + LBM_X) == x and i.u32(frame + lbm_base + LBM_Y) == y:
+                raise LbmAssembled  # the first context call after LBM::new's value has been moved into place
+            if create_slot[0] is None:
+                create_slot[0] = k  # the first context call made inline: Device::create_buffer (the colour buffer)
+            oid[0] += 1
+            if k != create_slot[0]:
+                # what follows LBM::new in the closure (surface configuration, the first frame): answered like a
+                # creation — (ObjectId, Box<dyn Any>) through the out pointer — until LBM's value is in place
+                other_slots.append(k)
+                struct.pack_into("<QII", i.mem, a[0], oid[0], 8, anyvt)
+                return None
+            # Device::create_buffer(&BufferDescriptor { label, size: u64, usage, mapped_at_creation }), inlined
+            d = a[-1]
+            buffers.append({"index": len(buffers), "how": f"create_buffer (context slot {k})", "object_id": oid[0],
+                            "descriptor_words": [i.u32(d + 4 * q) for q in range(6)]})
+            struct.pack_into("<QII", i.mem, a[0], oid[0], 8, anyvt)
+            return None
+        return h
+
+    for k in range(nslot):
+        inst.virtual_table[virt + k] = method(k)
+    for d in range(-256, 256):
+        inst.virtual_table[RC + d] = lambda i, *a: None
+    inst.hooks.update({loc["bgl"]: creator("bind_group_layout"), loc["pl"]: creator("pipeline_layout"),
+                       loc["shader"]: creator("shader_module"), loc["cpipe"]: creator("compute_pipeline"),
+                       loc["rpipe"]: creator("render_pipeline"), loc["buffer_init"]: create_buffer_init,
+                       loc["bg"]: create_bind_group})
+    for f in loc["drops"]:
+        inst.hooks[f] = lambda i, a: None
+    lbm_base = 168  # the `lbm` local of the closure's frame (checked below through x and y)
+    try:
+        inst.run_fragment(loc["f"], loc["start"], {loc["state_local"]: state, 4: frame})
+        raise AssertionError("the closure returned before LBM::new's value was seen")
+    except (LbmAssembled, Trap):
+        pass  # (a Trap: the first frame's render path, which the mock does not serve; the value is in place by then)
+    base = frame + lbm_base
+    assert (inst.u32(base + LBM_X), inst.u32(base + LBM_Y)) == (x, y) and not inst.called
+
+    def tag_at(addr):
+        t = inst.u32(addr)
+        return list(tags[t]) if t in tags else None
+
+    # the assembled LBM value: which tagged object sits at which field offset (24-byte objects; Vec {cap, ptr, len})
+    fields = {}
+    for off in range(0, 1400, 4):
+        t = tag_at(base + off)
+        if t and all(tag_at(base + off + 4 * q) == t for q in range(6)) and (off < 24 or tag_at(base + off - 4) != t or
+                                                                              (off - min(o for o in fields or [off])) % 24 == 0):
+            if not any(o < off < o + (SIZEOF_BUFFER if v[0] == "buffer" else 24) for o, v in fields.items()):
+                fields[off] = t
+    vecs = {}
+    for off in range(0, 1400, 4):  # Vec<BindGroup> / Vec<Vec<Buffer>>: ptr word at off, len right behind
+        ptr, ln = inst.u32(base + off), inst.u32(base + off + 4)
+        if ln == 2 and 0x1000 < ptr < len(inst.mem) - 48 and not arena <= ptr < arena + 64 * 512:
+            a, b = tag_at(ptr), tag_at(ptr + 24)
+            if a and b and a[0] == b[0] == "bind_group":
+                vecs[off] = [a[1], b[1]]
+    outer_ptr, outer_len = inst.u32(base + LBM_BUFFERS_PTR), inst.u32(base + LBM_BUFFERS_LEN)
+    assert outer_len == 2
+    data_buffers = []
+    for b in range(2):
+        p, ln = inst.u32(outer_ptr + 12 * b + 4), inst.u32(outer_ptr + 12 * b + 8)
+        assert ln == 9
+        data_buffers.append([tag_at(p + SIZEOF_BUFFER * k)[1] for k in range(9)])
+    return {"x": x, "y": y, "buffers": buffers, "bind_groups": groups, "created": created,
+            "lbm_fields": {str(k): v for k, v in sorted(fields.items())},
+            "lbm_bind_group_vecs": {str(k): v for k, v in sorted(vecs.items())}, "data_buffers": data_buffers}
+
+
 def presets_main(ref):
     out = {"wasm_sha256": np.bytes_(ref.sha256), "sizes": np.array(PRESET_SIZES, np.int64)}
     for x, y in PRESET_SIZES:
@@ -478,6 +676,13 @@ def presets_main(ref):
     path = os.path.join(HERE, "wasm_presets.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
+    import json
+    bg = bindgroup_trace(ref)
+    bg["wasm_sha256"] = ref.sha256
+    path = os.path.join(HERE, "wasm_bindgroups.json")
+    with open(path, "w") as f:
+        json.dump(bg, f, indent=1)
+    print(path, os.path.getsize(path), "bytes:", len(bg["buffers"]), "buffers,", len(bg["bind_groups"]), "bind groups")
 
 
 def main():

@@ -520,3 +520,127 @@ def test_cuda_presets_paint_what_the_reference_binary_draws(presets, name):
         np.testing.assert_array_equal(lbm.read_barrier(), want, err_msg=f"{name} on {x}x{y}")
         lbm.iterate(3)  # and the lattice steps with it
         lbm.close()
+
+
+# ---- the CONTENTS of the bind groups, from LBM::new as the binary itself runs it ---------------------------------------
+BINDGROUPS = os.path.join(HERE, "golden", "wasm_bindgroups.json")
+
+
+def ordered_driver_bindings(n, compute_step, stat, cmap):
+    """like recorded_driver, but per (group, binding): [(shader name, {(group, binding): identity})]"""
+    from oracle.wgsl_interp import REST, WgslLBM
+
+    class Recorder(WgslLBM):
+        def _load_shaders(self, root):
+            self.sh = {}
+
+        def identity(self, b):
+            for buf in (0, 1):
+                for k in range(9):
+                    if b is self.data[buf][k]:
+                        return ("rest",) if k == REST else ("population", buf, k)
+            for nm in ("ux", "uy", "rho", "output", "barrier", "colors"):
+                if b is getattr(self, nm):
+                    return (nm,)
+            return ("dims",) if isinstance(b, dict) else ("size",) if isinstance(b, np.uint32) else ("omega",)
+
+        def _run(self, name, bindings):
+            self.log.append((name, {gb: self.identity(b) for gb, b in bindings.items()}))
+
+        def color_map(self, name=None):
+            self._run(name or self.color_map_name, {(0, 0): self.colors, (1, 0): self.output, (2, 0): self.barrier,
+                                                    (3, 0): np.uint32(self.n)})
+
+    sim = Recorder(1.0, 8, 4)
+    sim.log = []
+    sim.compute_step = compute_step
+    sim.set_summary(Recorder.STATS[stat])
+    sim.iterate(n)
+    sim.color_map(Recorder.CMAPS[cmap])
+    return sim.log
+
+
+def test_bind_group_contents_equal_what_the_reference_binary_builds(golden):
+    """Which buffer sits at which binding of which bind group — `LBM::new`, lbm.rs:726-1049 — is no longer restated
+    by hand.  tests/golden/wasm_bindgroups.json is what the binary's own LBM::new did when it was executed inside the
+    start-up closure (its wgpu object creations served by the host, every object tagged): the buffers in creation order
+    with their contents, the entries of all bind groups, and where each buffer / bind group ends up in the assembled
+    LBM value.  Chained with the command stream of the binary's own LBM::iterate (which field it binds to which slot
+    of which pass), that gives, from the binary alone, the buffer behind every (group, binding) of every pass — which
+    must be what the oracle-side driver (the dispatch code all WGSL golden vectors were produced with) binds."""
+    import json
+    bg = json.load(open(BINDGROUPS))
+    assert bg["wasm_sha256"].encode() == bytes(golden["wasm_sha256"])
+    x, y = bg["x"], bg["y"]
+    bufs = bg["buffers"]
+    # -- what each buffer is, from its own creation: position in data_buffers, or contents
+    ident = {}
+    init = Oracle(1.25, 4, 4)  # any handle: set_equil lives in the library
+    from oracle.lbm_oracle import set_equil
+    eq = set_equil(0.1, 0.0, 1.0)
+    init.close()
+    for b in range(2):
+        for k in range(9):
+            n = bg["data_buffers"][b][k]
+            # LBM::new fills both sets from set_equil(0.1, 0, 1): x*y copies of the k-th value (lbm.rs:739-744)
+            assert bufs[n]["bytes"] == 4 * x * y and bufs[n]["uniform_contents"]
+            assert bufs[n]["first_word"] == int(np.float32(eq[k]).view(np.uint32)), (b, k)
+            ident[n] = ("rest",) if k == 4 and b == 0 else ("population", b, k)
+    assert bg["data_buffers"] == [list(range(9)), list(range(9, 18))]  # created set by set, k = 0..8
+    mask = np.zeros((y, x), np.uint32)
+    mask[0] = mask[-1] = 1
+    import hashlib
+    barrier = [b["index"] for b in bufs if b.get("sha256") == hashlib.sha256(mask.tobytes()).hexdigest()]
+    omega = [b["index"] for b in bufs if b.get("bytes") == 4 and b.get("usage") == 72 and b["index"] < 28]
+    size = [b["index"] for b in bufs if b.get("bytes") == 4 and b.get("first_word") == x * y]
+    dims = [b["index"] for b in bufs if b.get("sha256") == hashlib.sha256(np.array([x, y, x * y], np.uint32).tobytes()).hexdigest()]
+    assert len(barrier) == 1 and len(omega) == 1 and len(size) == 1 and len(dims) == 2  # compute + vertex copies
+    ident.update({barrier[0]: ("barrier",), omega[0]: ("omega",), size[0]: ("size",), dims[0]: ("dims",), dims[1]: ("dims",)})
+    groups = {g["index"]: g for g in bg["bind_groups"]}
+    # the zero-initialised storage buffers are told apart by the bind group LBM::new puts them in (lbm.rs:780-786:
+    # density_bg = three of them, output_bg = one, color_bg = one) and named as the shaders declare the bindings
+    fields = {int(k): v for k, v in bg["lbm_fields"].items()}
+    vecs = {int(k): v for k, v in bg["lbm_bind_group_vecs"].items()}
+    # -- chain with the command stream of LBM::iterate: per pass, slot -> LBM field -> bind group -> entries
+    stream = (json.loads(bytes(golden["iterate_trace/steps3_from0"]).decode()) +
+              json.loads(bytes(golden["iterate_trace/steps2_from7"]).decode()))
+    log = ordered_driver_bindings(3, 0, 0, 2) + ordered_driver_bindings(2, 7, 0, 2)
+    passes = [r for r in stream if r[0] == "pass"]
+    assert len(passes) == len(log) == 8 * 3 + 2 + 8 * 2 + 2
+    names = {}  # zero buffers: named on first sight by what the driver calls that (group, binding) ...
+    seen_groups = set()
+    for (_, label, _, slots, _), (shader, bound) in zip(passes, log):
+        got = {}
+        for slot, fld, idx in slots:
+            if idx is None:
+                kind, gi = fields[fld]
+                assert kind == "bind_group", (label, slot, fld)
+            else:
+                gi = vecs[fld][idx]
+            seen_groups.add(gi)
+            for binding, n in groups[gi]["entries"]:
+                who = ident.get(n)
+                if who is None:
+                    who = names.setdefault(n, bound[(slot, binding)])  # ... and must keep that name in every pass
+                got[(slot, binding)] = who
+        assert got == bound, (label or shader, got, bound)
+    assert sorted(names.values()) == [("colors",), ("output",), ("rho",), ("ux",), ("uy",)] and len(names) == 5
+    # the rest population is bound from buffer set 0 only (lbm.rs:775-778): data_buffers[1][4] is in no bind group
+    dead = bg["data_buffers"][1][4]
+    assert all(n != dead for g in groups.values() for _, n in g["entries"])
+    assert [e for e in groups[8]["entries"]] == [[0, size[0]], [1, omega[0]], [2, bg["data_buffers"][0][4]]]
+    # every bind group LBM::iterate uses was reached (the draw group and the vertex dimensions belong to paint / render)
+    assert seen_groups == set(range(16)) - {14}
+
+
+@needs_reference
+def test_bind_group_fixture_reruns_live(golden):
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_wasm_golden as gen
+    ref = gen.Reference()
+    live = gen.bindgroup_trace(ref)
+    stored = json.load(open(BINDGROUPS))
+    for key in ("buffers", "bind_groups", "lbm_fields", "lbm_bind_group_vecs", "data_buffers", "created"):
+        assert live[key] == stored[key], key
