@@ -112,6 +112,25 @@ impl LBM {
         check(unsafe { sys::blbm_single_cell(self.h, index as u32) });
         self.compute_step = 0;
     }
+    /// lbm.rs:1367 / :1372 / :1388 — the barrier presets (thick lines through the library's rasteriser)
+    pub fn curl_barrier(&mut self, _driver: &Driver) {
+        check(unsafe { sys::blbm_curl_barrier(self.h) });
+    }
+    pub fn chaos_barrier(&mut self, _driver: &Driver) {
+        check(unsafe { sys::blbm_chaos_barrier(self.h) });
+    }
+    pub fn welcome_barrier(&mut self, _driver: &Driver) {
+        check(unsafe { sys::blbm_welcome_barrier(self.h) });
+    }
+    /// lbm.rs:1299 — colour-map the output field on the device (Inferno 0, Viridis 1, Jet 2; lbm.rs:18-24)
+    pub fn color_map(&mut self, map: i32) {
+        check(unsafe { sys::blbm_color_map(self.h, map) });
+    }
+    pub fn read_colors(&mut self) -> Vec<f32> {
+        let mut v = vec![0f32; self.x as usize * self.y as usize * 3];
+        check(unsafe { sys::blbm_read_colors(self.h, v.as_mut_ptr()) });
+        v
+    }
     /// lbm.rs:1166
     pub fn get_frame_num(&self) -> usize {
         unsafe { sys::blbm_get_frame_num(self.h) as usize }
