@@ -90,10 +90,10 @@ def mask_rows(kind, w, h_total, r0, r1, discs=()):
     return r0, m
 
 
-def workload_config(name, world):
+def workload_config(name, world, strong=None):
     """The `config` object of the JSON line: the workload only — identical in both arms (ours and --impl reference)."""
     w, rows_gpu, omega, u0, kind = WORKLOADS[name]
-    strong = name in STRONG
+    strong = name in STRONG if strong is None else strong
     h_total = rows_gpu if strong else rows_gpu * world
     per_gpu = h_total // world
     resident = w * per_gpu * 18 * 4  # the two population lattices alone
@@ -225,7 +225,7 @@ def run_reference(args):
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         use_all_cores()  # torchrun exported OMP_NUM_THREADS=1; the other ranks have exited, rank 0 owns the host
     w, rows_gpu, omega, u0, kind = WORKLOADS[args.workload]
-    if args.workload in STRONG:
+    if args.workload in STRONG or args.strong:
         rows_gpu //= max(1, args.gpus)
     # calibrate, then bound the sample so that (steps + warmup) steps take at most about four minutes
     calib_rows = max(16, (4 << 20) // w)
@@ -260,9 +260,9 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "MLUPS (D2Q9 fp32)", "value": val, "unit": "MLUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if (args.workload in STRONG or args.strong) else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
+        "config": workload_config(args.workload, args.gpus, args.workload in STRONG or args.strong),
         "implementation": {"kernel": "cpu oracle (8 passes per step)", "parallelism": f"{threads()} host threads"},
         "cpu_baseline": {"value": val, "unit": "MLUPS", "cores": threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -617,6 +617,8 @@ def main():
     ap.add_argument("--link-in-kernel", type=int, default=-1,
                     help="linked slabs: halo epoch handshake inside the step kernel (1, default) or by wait/signal kernels (0)")
     ap.add_argument("--lazy", type=int, default=-1, help="barrier-chain table: 0 never, 1 always, 2 auto (default)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling of any workload: the lattice of the N = 1 case is split into N slabs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check (N > 1)")
@@ -633,7 +635,7 @@ def main():
     job = Job(args)
     n = job.ngpu
     w, rows_gpu, omega, u0, kind = WORKLOADS[args.workload]
-    strong = args.workload in STRONG
+    strong = args.workload in STRONG or args.strong
     h_total = rows_gpu if strong else rows_gpu * n
 
     parity = None
@@ -677,7 +679,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": t["ms"] / args.steps, "higher_is_better": True,
         "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, n),
+        "config": workload_config(args.workload, n, strong),
         "implementation": {"kernel": kname, "halo_handshake": (None if n == 1 else "wait/signal kernels" if args.link_in_kernel == 0
                                                                else "inside the step kernel"),
                            "parallelism": (f"y-slabs x{n}, one blbm_create_group handle in one process" if job.single
