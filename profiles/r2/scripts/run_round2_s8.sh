@@ -8,7 +8,8 @@ mkdir -p gpurun_out
 port=29560
 for wl in cavity4096 cylinder512; do
   python bench.py --gpus 1 --workload $wl --steps 400 --warmup 40 --no-cpu-baseline --no-e2e --graphs 0 > gpurun_out/r2s8_${wl}_n1.json 2>> gpurun_out/r2s8.err
-  for n in 2 4 8; do
+  ns="2 4 8"; [ $wl = cylinder512 ] && ns="8"
+  for n in $ns; do
     for mode in 1 0; do
       port=$((port+1))
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --workload $wl --strong \
