@@ -632,6 +632,8 @@ def main():
         run_reference(args)
         return
 
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        args.single_process = True  # launched without torchrun: one process drives all N GPUs through a group handle
     job = Job(args)
     n = job.ngpu
     w, rows_gpu, omega, u0, kind = WORKLOADS[args.workload]
