@@ -52,13 +52,102 @@ def test_twin_libraries_are_built_and_export_the_same_abi():
         assert hasattr(lib, name), name
 
 
+WGSL_ROOT = "/root/reference/lbm-wgpu/src/rewritten_shaders"
+needs_reference = pytest.mark.skipif(not os.path.isdir(WGSL_ROOT), reason="/root/reference is only present in the build container")
+
+
+def _twin_env():
+    return dict(os.environ, LBM_ORACLE_CONTRACT="1", BLBM_LIBRARY=os.path.join(ROOT, "lbm_b200", "libblbm_contract.so"))
+
+
+def test_twin_oracle_reproduces_the_shader_text_executed_under_contraction():
+    """tests/golden/wgsl_contract.npz = the reference's WGSL text executed with the fusions DERIVED from that text
+    (oracle/wgsl_contract.py) on the scenarios of tests/wgsl_cases.py; the twin oracle — whose fma pairs were written
+    down by hand — must reproduce every buffer of every snapshot and the colour maps bit for bit (test_wgsl_pin.py run
+    in a child process that loads the twin)."""
+    sel = "oracle_reproduces_the_interpreted_reference_shaders or oracle_colour_maps_reproduce"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_wgsl_pin.py"), "-m", "not gpu",
+                        "-q", "-x", "-k", sel, "-p", "no:cacheprovider"], env=_twin_env(), capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@needs_reference
+def test_the_fused_pairs_are_derived_from_the_shader_text():
+    """value numbering + use counting over each shader's main (oracle/wgsl_contract.py): the additions that fuse a
+    single-use multiply are exactly the pairs both twin builds spell out by hand — per relaxation `f += w*(k*(p-u215)-f)`
+    a subtract fusing its left and an add fusing its right operand, `u2` in the corner shader only, one each in
+    rho.wgsl and speed.wgsl, one vec3 sum per colour-map segment — and nothing in the pre-collision, stream, curl,
+    ux / uy and barrier shaders."""
+    import json
+    from oracle import wgsl_contract
+    live = {k: [list(p) for p in v] if isinstance(v, list) else v for k, v in wgsl_contract.fusion_table().items()}
+    assert live == json.load(open(os.path.join(ROOT, "tests", "golden", "wgsl_contract_fusions.json")))
+    relax = [["-", "lhs"], ["+", "rhs"]]
+    assert live["collision/cardinal_collision.wgsl"] == relax * 5
+    assert live["collision/corner_collision.wgsl"] == [["+", "lhs"]] + relax * 4
+    assert live["summary_stats/rho.wgsl"] == [["-", "lhs"]] and live["summary_stats/speed.wgsl"] == [["+", "lhs"]]
+    assert [len(live[f"color_map/{m}.wgsl"]) for m in ("inferno", "viridis", "jet")] == [4, 4, 8]
+    assert all(v == [] for k, v in live.items() if k.split("/")[0] in ("pre_collision", "stream", "update_barrier"))
+    assert live["summary_stats/curl.wgsl"] == live["summary_stats/ux.wgsl"] == live["summary_stats/uy.wgsl"] == []
+
+
+def _contract_soak_seeds():
+    extra = os.environ.get("BLBM_WGSL_CONTRACT_SOAK")  # e.g. "100-199"
+    if extra:
+        a, _, b = extra.partition("-")
+        return list(range(int(a), int(b or a) + 1))
+    return list(range(6))
+
+
+@needs_reference
+@pytest.mark.parametrize("seed", _contract_soak_seeds())
+def test_twin_oracle_against_the_live_shaders_under_contraction_on_random_scripts(seed):
+    from oracle.lbm_oracle import Oracle
+    from oracle.wgsl_contract import WgslLBMContract
+    from tests import wgsl_cases
+    from tests.test_wgsl_pin import oracle_snapshot
+    from tests.util import assert_same_bits, random_script
+    rng = np.random.default_rng(515151 + seed)
+    w, h = int(rng.integers(3, 140)), int(rng.integers(3, 70))
+    omega = float(rng.choice([1.0 / (3 * 0.02 + 0.5), 1.25, 1.0, 1.9, 0.6]))
+    u0 = float(rng.choice([0.1, 0.05, 0.0, 0.17]))
+    script = random_script(rng, w, h, phases=int(rng.integers(3, 7)), max_steps=int(rng.integers(5, 40)))
+    sim = WgslLBMContract(omega, w, h, inflow_ux=u0)
+    o = Oracle(omega, w, h, inflow_ux=u0, contract=True)
+    a = wgsl_cases.replay(script, sim, lambda s: s.state())
+    b = wgsl_cases.replay(script, o, oracle_snapshot)
+    o.close()
+    assert len(a) == len(b) > 0
+    for i, (sa, sb) in enumerate(zip(a, b)):
+        for k in wgsl_cases.STATE_KEYS:
+            assert_same_bits(np.asarray(sb[k]).reshape(np.asarray(sa[k]).shape), sa[k],
+                             f"seed {seed} ({w}x{h}, omega {omega:.4f}, u0 {u0}) snapshot {i} {k}")
+
+
+def test_fma32_is_the_correctly_rounded_fused_multiply_add():
+    """the executor's fma (exact product in f64, sum rounded to odd, then to f32) against exact rational arithmetic,
+    on operands chosen for heavy cancellation"""
+    from fractions import Fraction
+    from oracle.wgsl_contract import fma32
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal(3000).astype(np.float32)
+    b = rng.standard_normal(3000).astype(np.float32)
+    c = (-(a.astype(np.float64) * b.astype(np.float64)) * (1 + rng.standard_normal(3000) * 1e-7)).astype(np.float32)
+    got = fma32(a, b, c)
+    for x, y, z, g in zip(a, b, c, got):
+        exact = Fraction(float(x)) * Fraction(float(y)) + Fraction(float(z))
+        d = abs(Fraction(float(g)) - exact)
+        for nb in (np.nextafter(g, np.float32(-np.inf)), np.nextafter(g, np.float32(np.inf))):
+            assert d <= abs(Fraction(float(nb)) - exact)
+
+
 @pytest.mark.gpu
 def test_parity_suite_passes_on_the_twin_pair():
     """the CUDA twin against the oracle twin: random API scripts on every kernel, config 1 at full length on the
     default kernel, the summary statistics and colour maps, slab groups — all bit for bit, in a child process that
     loads the twin libraries instead of the default pair"""
-    env = dict(os.environ, LBM_ORACLE_CONTRACT="1",
-               BLBM_LIBRARY=os.path.join(ROOT, "lbm_b200", "libblbm_contract.so"))
+    env = _twin_env()
     sel = ("test_random_scripts_bit_exact or test_create_state or (test_config1_cylinder and Vec4 and 0.02) or "
            "test_color_maps or test_slab_group_on_one_device or test_chain_table_settles or test_api_fuzz_against_oracle")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
@@ -66,3 +155,9 @@ def test_parity_suite_passes_on_the_twin_pair():
                        timeout=1500, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+    # ... and the CUDA twin against the shader text executed under the derived contraction (wgsl_contract.npz)
+    sel = "cuda_reproduces_the_interpreted_reference_shaders or cuda_colour_maps_reproduce"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_wgsl_pin.py"), "-m", "gpu",
+                        "-q", "-x", "-k", sel, "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
