@@ -330,7 +330,9 @@ int run_summary(blbm *h)
     return BLBM_OK;
 }
 
-constexpr uint32_t GRAPH_LEN[blbm::GRAPH_SIZES] = {16, 8, 4, 2};  // all even: a call's runs share one start parity
+// all even: a call's runs share one start parity; every even length, so that the 14 graph-able steps of a 15-step
+// frame are one launch instead of three (8 + 4 + 2)
+constexpr uint32_t GRAPH_LEN[blbm::GRAPH_SIZES] = {16, 14, 12, 10, 8, 6, 4, 2};
 
 bool graphs_wanted(const blbm *h)
 {
@@ -344,15 +346,18 @@ void drop_step_graphs(blbm *h)
     for (auto &par : h->graph)
         for (auto &cls : par)
             for (auto &pend : cls)
-                for (cudaGraphExec_t &g : pend)
-                    if (g) {
-                        cudaGraphExecDestroy(g);
-                        g = nullptr;
-                    }
+                for (auto &tail : pend)
+                    for (cudaGraphExec_t &g : tail)
+                        if (g) {
+                            cudaGraphExecDestroy(g);
+                            g = nullptr;
+                        }
     h->graphs_primed = false;
 }
 
-// capture every run length for both start parities and both class buffers under the current kernel configuration
+// capture every run length for both start parities and both class buffers under the current kernel configuration,
+// without and with the moment-storing step that ends a call (tail; not with the chain table, whose moment rows
+// are launch parameters of that step)
 int prime_step_graphs(blbm *h)
 {
     drop_step_graphs(h);
@@ -362,6 +367,7 @@ int prime_step_graphs(blbm *h)
     for (int par = 0; par < 2 && rc == BLBM_OK; par++)
         for (int cls = 0; cls < 2 && rc == BLBM_OK; cls++)
           for (int pend = 0; pend < 2 && rc == BLBM_OK; pend++)
+           for (int tail = 0; tail < (h->chain_active ? 1 : 2) && rc == BLBM_OK; tail++)
             for (int q = 0; q < blbm::GRAPH_SIZES && rc == BLBM_OK; q++) {
                 cudaGraph_t graph = nullptr;
                 cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
@@ -371,18 +377,18 @@ int prime_step_graphs(blbm *h)
                 }
                 h->step = (uint64_t)par;
                 h->cls_cur = cls;
-                for (uint32_t k = 0; k < GRAPH_LEN[q] && rc == BLBM_OK; k++) {
+                for (uint32_t k = 0; k < GRAPH_LEN[q] + (uint32_t)tail && rc == BLBM_OK; k++) {
                     const int x = (int)((h->step + 1) % 2), y = (int)(h->step % 2);
-                    rc = launch_step(h, MODE_FUSED, x, y, false);
+                    rc = launch_step(h, MODE_FUSED, x, y, k == GRAPH_LEN[q]);
                     h->step++;
                     if (pend && k == 0) h->cls_cur ^= 1;  // the pending stream saw the old classification; swap
                 }
                 e = cudaStreamEndCapture(h->stream, &graph);
                 if (rc == BLBM_OK && e != cudaSuccess) rc = fail(BLBM_ECUDA, "stream capture failed: %s", cudaGetErrorString(e));
                 if (rc == BLBM_OK) {
-                    e = cudaGraphInstantiate(&h->graph[par][cls][pend][q], graph, 0);
+                    e = cudaGraphInstantiate(&h->graph[par][cls][pend][tail][q], graph, 0);
                     if (e != cudaSuccess) {
-                        h->graph[par][cls][pend][q] = nullptr;
+                        h->graph[par][cls][pend][tail][q] = nullptr;
                         rc = fail(BLBM_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
                     }
                 }
@@ -425,12 +431,13 @@ int ensure_step_graphs(blbm *h, bool *usable)
     return BLBM_OK;
 }
 
-// GRAPH_LEN[q] fused, non-moment-storing steps starting at the current parity, as one graph launch
-int run_step_graph(blbm *h, int q)
+// GRAPH_LEN[q] fused, non-moment-storing steps starting at the current parity (and, with tail, the moment-storing
+// step after them), as one graph launch
+int run_step_graph(blbm *h, int q, bool tail)
 {
-    CK(cudaGraphLaunch(h->graph[h->step % 2][h->cls_cur][h->cls_pending ? 1 : 0][q], h->stream));
-    h->step += GRAPH_LEN[q];
-    h->launches += GRAPH_LEN[q];
+    CK(cudaGraphLaunch(h->graph[h->step % 2][h->cls_cur][h->cls_pending ? 1 : 0][tail ? 1 : 0][q], h->stream));
+    h->step += GRAPH_LEN[q] + (tail ? 1u : 0u);
+    h->launches += GRAPH_LEN[q] + (tail ? 1u : 0u);
     consume_pending_class(h);  // (its first step ran on the old class buffer)
     return BLBM_OK;
 }
@@ -465,8 +472,10 @@ int do_steps(blbm *h, uint32_t n, bool store_moments = true)
         if (graph_state == 1 && h->regimeT && left - 1 >= GRAPH_LEN[blbm::GRAPH_SIZES - 1]) {
             int q = 0;
             while (GRAPH_LEN[q] > left - 1) q++;
-            if ((rc = run_step_graph(h, q)) != BLBM_OK) return rc;
-            left -= GRAPH_LEN[q];
+            // the call ends with this run and its moment-storing step: one launch for both
+            const bool tail = store_moments && !h->chain_active && left - 1 == GRAPH_LEN[q];
+            if ((rc = run_step_graph(h, q, tail)) != BLBM_OK) return rc;
+            left -= GRAPH_LEN[q] + (tail ? 1u : 0u);
             continue;
         }
         if (!h->regimeT) {
@@ -1148,9 +1157,18 @@ int blbm_draw_points64(blbm_t *h, const uint64_t *pairs, size_t npairs)
         // small stroke, no chain table to evict from: the pairs go as kernel arguments, no upload
         SmallPaint sp;
         memcpy(sp.v, uniq.data(), nu * 2 * sizeof(uint64_t));
-        CK(launch_mask_scatter_args(h->mask, geom(h), sp, (uint32_t)nu, h->stream));
+        int target;
+        uint32_t blo, bhi;
+        if (plan_class_rebuild(h, rlo, rhi, false, &target, &blo, &bhi)) {
+            // mask update and class rebuild in ONE launch (a paint was two launches of ~5 us on a lattice whose
+            // 15-step frame is 60 us)
+            CK(launch_paint_small(h->mask, geom(h), sp, (uint32_t)nu, h->cls[target], h->rowflag[target], blo, bhi,
+                                  h->stream));
+        } else {
+            CK(launch_mask_scatter_args(h->mask, geom(h), sp, (uint32_t)nu, h->stream));  // halo rows only
+        }
         h->launches++;
-        return rebuild_class(h, rlo, rhi, false);
+        return BLBM_OK;
     }
     if (nu) {
         if (h->d_pairs_cap < nu) {

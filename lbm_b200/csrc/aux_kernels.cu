@@ -173,8 +173,9 @@ __global__ void build_class_kernel(uint16_t *cls, const uint8_t *mask, const Sla
 
 // A small paint: the (location, value) pairs travel as kernel arguments, which saves the upload of the general path
 // (small lattices are launch-bound: a 15-step frame of the 512 x 256 cylinder is 60 us, the upload 3 us of it).
-// (Fusing the class rebuild into the same single-block launch was measured and rejected: one SM rebuilding 13 rows
-// takes longer than a second launch spread over the chip, 14.4 vs 11.4 us per paint.)
+// (Fusing the class rebuild into the same SINGLE-BLOCK launch was measured and rejected: one SM rebuilding 13 rows
+// takes longer than a second launch spread over the chip, 14.4 vs 11.4 us per paint; paint_small_kernel below fuses
+// them across many blocks instead.)
 __global__ void mask_scatter_args_kernel(uint8_t *mask, const SlabGeom g, const SmallPaint pairs, const uint32_t npairs)
 {
     if (threadIdx.x >= npairs) return;
@@ -191,6 +192,42 @@ cudaError_t launch_mask_scatter_args(uint8_t *mask, const SlabGeom &g, const Sma
     if (npairs == 0) return cudaSuccess;
     if (npairs > SMALL_PAINT_PAIRS) return cudaErrorInvalidValue;
     mask_scatter_args_kernel<<<1, SMALL_PAINT_PAIRS, 0, st>>>(mask, g, pairs, npairs);
+    return cudaGetLastError();
+}
+
+static unsigned class_grid(const SlabGeom &g, uint32_t nrows);
+
+// Small paint and class rebuild in one launch, without a grid-wide barrier between the two: EVERY block applies the
+// whole (at most 64-pair, already de-duplicated) stroke to the mask itself - all blocks store the same bytes to the
+// same places - and, after a block barrier, rebuilds its share of the class words from a mask that holds the stroke
+// wherever it looks: its own stores are visible to it, and anybody else's store to those bytes has the same value.
+__global__ void __launch_bounds__(256) paint_small_kernel(uint8_t *mask, const SlabGeom g, const SmallPaint pairs,
+                                                          const uint32_t npairs, uint16_t *cls, uint8_t *rowflag,
+                                                          const uint32_t row_begin, const uint32_t row_end)
+{
+    if (threadIdx.x < npairs) {
+        const uint64_t loc = pairs.v[2 * threadIdx.x], val = pairs.v[2 * threadIdx.x + 1];
+        const uint64_t gy = loc / g.W;
+        const int64_t lr = (int64_t)gy - (int64_t)g.row0;
+        if (gy < g.Hg && lr >= -2 && lr < (int64_t)g.rows + 2)
+            mask[mask_row_off(lr, g.P) + (uint32_t)(loc - gy * g.W)] = (val == 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    const uint32_t nchunk = (g.P + CHUNK - 1) / CHUNK;
+    const size_t nwarps_total = (size_t)(row_end - row_begin) * nchunk;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < nwarps_total;
+         wid += ((size_t)gridDim.x * blockDim.x) >> 5)
+        build_class_chunk<false>(cls, mask, g, nullptr, rowflag, row_begin + (uint32_t)(wid / nchunk),
+                                 (uint32_t)(wid % nchunk), nchunk, lane);
+}
+
+cudaError_t launch_paint_small(uint8_t *mask, const SlabGeom &g, const SmallPaint &pairs, uint32_t npairs, uint16_t *cls,
+                               uint8_t *rowflag, uint32_t row_begin, uint32_t row_end, cudaStream_t st)
+{
+    if (npairs == 0 || npairs > SMALL_PAINT_PAIRS || row_end <= row_begin) return cudaErrorInvalidValue;
+    paint_small_kernel<<<class_grid(g, row_end - row_begin), 256, 0, st>>>(mask, g, pairs, npairs, cls, rowflag, row_begin,
+                                                                           row_end);
     return cudaGetLastError();
 }
 
@@ -968,6 +1005,7 @@ cudaError_t preload_aux_kernels()
     BLBM_TOUCH(build_class_kernel<false>);
     BLBM_TOUCH(build_class_kernel<true>);
     BLBM_TOUCH(mask_scatter_args_kernel);
+    BLBM_TOUCH(paint_small_kernel);
     BLBM_TOUCH(precollision_moments_kernel);
     BLBM_TOUCH(curl_vec4_kernel);
     BLBM_TOUCH(summary_kernel<0>);

@@ -377,6 +377,10 @@ struct SmallPaint {
 };
 cudaError_t launch_mask_scatter_args(uint8_t *mask, const SlabGeom &g, const SmallPaint &pairs, uint32_t npairs,
                                      cudaStream_t st);
+// the same mask update and the rebuild of the class words of owned rows [row_begin, row_end) in one launch (no chain
+// table: there is nothing to keep)
+cudaError_t launch_paint_small(uint8_t *mask, const SlabGeom &g, const SmallPaint &pairs, uint32_t npairs, uint16_t *cls,
+                               uint8_t *rowflag, uint32_t row_begin, uint32_t row_end, cudaStream_t st);
 // the public class words of blbm_read_cell_class, densely packed rows x W
 cudaError_t launch_build_public_class(uint16_t *dst, const uint8_t *mask, const SlabGeom &g, cudaStream_t st);
 cudaError_t launch_precollision_moments(const float *const *f8, float *mx, float *my, float *rho, uint32_t W,

@@ -121,13 +121,15 @@ struct blbm_handle {
     bool chain_unsettle = false;       // omega changed: settled chains must be recomputed by the next replay
     unsigned long long *chain_counter = nullptr;
     unsigned long long *mailbox_host = nullptr, *mailbox_dev = nullptr;  // mapped pinned word for small results
-    // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): runs of 16, 8, 4 and 2 fused,
-    // non-moment-storing steps are captured into CUDA graphs — all four lengths for both start parities, both
-    // class buffers, and with / without a class swap pending after the first step (the step after a paint) at once,
-    // the first time a run is wanted (a couple of milliseconds, in the caller's first iterate), so that no capture
-    // ever lands inside a frame loop — and re-captured when omega, the kernel shape or the chain table change.
-    static constexpr int GRAPH_SIZES = 4;  // 16, 8, 4, 2
-    cudaGraphExec_t graph[2][2][2][GRAPH_SIZES] = {};  // [start parity][class buffer][swap pending][length index]
+    // Small lattices are launch-bound (512x256: ~2.5 us of kernel per step): runs of 2, 4, .. 16 fused steps are
+    // captured into CUDA graphs - every even length, for both start parities, both class buffers, with / without a
+    // class swap pending after the first step (the step after a paint), and without / with the moment-storing step
+    // that ends a call (so that the 15 steps of a frame are ONE launch) - all at once, the first time a run is wanted
+    // (a few milliseconds, in the caller's first iterate), so that no capture ever lands inside a frame loop; they
+    // are re-captured when omega, the kernel shape or the chain table change.
+    static constexpr int GRAPH_SIZES = 8;  // every even run length up to 16
+    // [start parity][class buffer][swap pending][+ the call's moment-storing last step][length index]
+    cudaGraphExec_t graph[2][2][2][2][GRAPH_SIZES] = {};
     unsigned long long graph_sig[4] = {0, 0, 0, 0}, graph_pending_sig[4] = {0, 0, 0, 0};
     bool graphs_primed = false;
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)

@@ -665,6 +665,51 @@ def test_paint_frames_never_synchronise_and_stay_exact():
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("w,h", [(150, 40), (256, 33)])
+def test_every_graph_run_length_with_and_without_the_moment_tail(kernel, w, h):
+    """Small lattices replay runs of 2, 4 .. 16 steps as CUDA graphs, the call's moment-storing last step included when
+    the run ends the call and not when it does not (longer calls); a stroke of at most 64 cells is
+    ONE launch that updates the mask and rebuilds the class words (every block applies the whole stroke before it reads
+    the mask), leaving a class swap pending for the first step of the next graph.  Calls of every length 1..35 from
+    both start parities, with and without such a stroke in front, strokes on the inlet / outlet columns and on rows
+    0 / H-1 and repeated cells (last writer wins), against the oracle after every call."""
+    om = omega_from_viscosity(0.02)
+    lbm, ora = LBM(om, w, h, inflow_ux=0.08, kernel=kernel, lazy_barriers=0), Oracle(om, w, h, inflow_ux=0.08)
+    rng = np.random.default_rng(w)
+    lbm.iterate(1); ora.iterate(1)  # the graphs are captured by the first call that could use one: make it this one
+    lbm.iterate(5); ora.iterate(5)
+    lengths = list(range(1, 36)) + [17, 15, 15, 16, 3, 2]
+    for k, n in enumerate(lengths):
+        if k % 3 != 2:
+            m = int(rng.integers(1, 65))
+            loc = rng.integers(0, w * h, size=m)
+            if k % 6 == 0:
+                loc[: m // 2] = (rng.integers(0, h, size=m // 2)) * w + rng.choice([0, w - 1], size=m // 2)
+            if m > 3:
+                loc[1] = loc[0]  # the same cell twice in one stroke
+            val = rng.integers(0, 2, size=m)
+            pairs = np.stack([loc, val], 1).astype(np.uint32)
+            lbm.draw_points(pairs); ora.draw_points(pairs)
+            if k % 9 == 4:  # two strokes before the same step
+                pairs2 = np.stack([loc[::-1], 1 - val], 1).astype(np.uint32)[: max(1, m // 3)]
+                lbm.draw_points(pairs2); ora.draw_points(pairs2)
+        if k % 4 == 1:
+            lbm.advance(n)  # steps (moments of the last one stored) without the summary launch
+            for _ in range(n):
+                ora.step()
+            for got, want, what in zip(lbm.read_moments(), ora.moments(), ("mx", "my", "rho")):
+                assert_same_bits(got, want, f"{what} after advance({n}), call {k}")
+        else:
+            lbm.iterate(n); ora.iterate(n)
+            compare_state(lbm, ora, f"graph runs: iterate({n}), call {k}", populations=(k % 5 == 0))
+    lbm.update_omega_buffer(1.3); ora.update_omega_buffer(1.3)  # a changed configuration: graph-less, then re-captured
+    for n in (15, 15, 15, 8):
+        lbm.iterate(n); ora.iterate(n)
+    compare_state(lbm, ora, "after the omega change")
+    lbm.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("omega", [1.0, 1.0 / (3 * 0.02 + 0.5)])
 def test_chain_table_settles_unsettles_and_evicts_exactly(kernel, omega):
     """The ordered barrier-chain table through its whole life on a 15 % porous lattice: chains settle on their exact
