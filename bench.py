@@ -345,7 +345,8 @@ class Job:
             del m
         if args.block_rows:
             lbm.set_tuning(0, args.block_rows)
-        for knob, val in ((4, args.dense), (5, args.graphs), (6, args.packed), (7, args.index32), (8, args.link_in_kernel)):
+        for knob, val in ((4, args.dense), (5, args.graphs), (6, args.packed), (7, args.index32), (8, args.link_in_kernel),
+                          (9, args.pdl)):
             if val >= 0:
                 lbm.set_tuning(knob, val)
         return lbm, r0, r1
@@ -616,6 +617,8 @@ def main():
     ap.add_argument("--index32", type=int, default=-1, help="vec4 32-bit plane offsets: -1 auto, 0, 1")
     ap.add_argument("--link-in-kernel", type=int, default=-1,
                     help="linked slabs: halo epoch handshake inside the step kernel (1, default) or by wait/signal kernels (0)")
+    ap.add_argument("--pdl", type=int, default=-1,
+                    help="programmatic dependent launch of the fused step: -1 auto (on outside CUDA graphs), 0, 1")
     ap.add_argument("--lazy", type=int, default=-1, help="barrier-chain table: 0 never, 1 always, 2 auto (default)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling of any workload: the lattice of the N = 1 case is split into N slabs")

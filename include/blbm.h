@@ -263,10 +263,13 @@ typedef enum blbm_tune {
                                       2 dense + own-row vectors staged in shared memory with cp.async (what auto
                                       picks wherever the barrier-chain table is active), 3 as 2 with the class
                                       words read without the chunk-flag test */
-    BLBM_TUNE_CUDA_GRAPHS = 5,     /* replay 8 steps per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
+    BLBM_TUNE_CUDA_GRAPHS = 5,     /* replay runs of 2..16 steps (and a call's moment-storing last step) per CUDA-graph launch: -1 auto (lattices <= 4 Mi cells), 0, 1 */
     BLBM_TUNE_VEC4_PACKED = 6,     /* collide cell pairs with packed fp32 adds (sm_100 FADD2): 0 (default) or 1; same bits,
                                       measured slower (register pressure) */
     BLBM_TUNE_VEC4_INDEX32 = 7,    /* 32-bit plane offsets where a plane has < 2^32 elements: -1 auto (default, = 1), 0, 1 */
+    BLBM_TUNE_PDL = 9,             /* programmatic dependent launch of the fused vec4 step (its blocks are scheduled while the
+                                      previous step drains): -1 auto (default: on, except inside the CUDA graphs of small lattices), 0, 1;
+                                      unlinked handles only */
     BLBM_TUNE_LINK_IN_KERNEL = 8   /* linked slabs: 1 (default) the fused step kernel waits for / publishes the halo
                                       epochs itself (face row blocks first, interior rows overlap the exchange);
                                       0 one-thread wait and signal kernels around every launch */

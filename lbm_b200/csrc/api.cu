@@ -211,6 +211,8 @@ int chain_try_enter(blbm *h, uint32_t steps_left)
     return BLBM_OK;
 }
 
+bool graphs_wanted(const blbm *h);
+
 int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
 {
     StepParams p;
@@ -280,7 +282,11 @@ int launch_step(blbm *h, int mode, int xbuf, int ybuf, bool mom)
             // 32-bit plane offsets wherever the slab allows it (always on a B200 at the default block shape): one
             // IMAD.WIDE per address, and the variants that then stay at 64 registers without a spill
             const bool index32 = h->vec4_index32 != 0;
-            e = launch_step_vec4(p, mode, mom, h->vec4_rows, flavour, h->vec4_packed != 0, index32, h->stream);
+            // stream-ordered steps: let the next step's blocks be scheduled while this one drains (4096^2: +1.2 %).
+            // Not inside the graphs of small lattices: programmatic edges made their replay slower (4.7 vs 4.1 us
+            // per step, profiles/r2/r2u_*)
+            const bool pdl = !any_peer(h) && (h->use_pdl < 0 ? !graphs_wanted(h) : h->use_pdl != 0);
+            e = launch_step_vec4(p, mode, mom, h->vec4_rows, flavour, h->vec4_packed != 0, index32, pdl, h->stream);
         }
         break;
     }
@@ -416,7 +422,8 @@ int ensure_step_graphs(blbm *h, bool *usable)
         1, omega_bits,
         (unsigned long long)h->kernel | ((unsigned long long)h->vec4_rows << 8) |
             ((unsigned long long)(h->vec4_dense + 1) << 16) | ((unsigned long long)h->chain_active << 24) |
-            ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)(h->vec4_index32 + 1) << 26),
+            ((unsigned long long)h->vec4_packed << 25) | ((unsigned long long)(h->vec4_index32 + 1) << 26) |
+            ((unsigned long long)(h->use_pdl + 1) << 28),
         (unsigned long long)(uintptr_t)h->pool};
     *usable = true;
     if (h->graphs_primed && memcmp(h->graph_sig, sig, sizeof(sig)) == 0) return BLBM_OK;
@@ -1570,6 +1577,10 @@ int blbm_set_tuning(blbm_t *h, int knob, int value)
     case BLBM_TUNE_CUDA_GRAPHS:
         if (value < -1 || value > 1) return fail(BLBM_EINVAL, "graphs must be -1 (auto), 0 or 1");
         h->use_graphs = value;
+        return BLBM_OK;
+    case BLBM_TUNE_PDL:
+        if (value < -1 || value > 1) return fail(BLBM_EINVAL, "dependent launch must be -1 (auto), 0 or 1");
+        h->use_pdl = value;
         return BLBM_OK;
     default: return fail(BLBM_EINVAL, "unknown tuning knob %d", knob);
     }

@@ -346,8 +346,9 @@ cudaError_t launch_step_scalar(const StepParams &p, int mode, bool store_moments
 // index32: use 32-bit plane offsets where the slab allows it
 // p.link.sig_epoch != 0 selects the variant with the in-kernel neighbour handshake (fused mode only; needs
 // vec4_links_in_kernel(block_rows, packed))
+// pdl: launch with the programmatic-serialization attribute (unlinked launches only; see pdl_wait in kernels.cu)
 cudaError_t launch_step_vec4(const StepParams &p, int mode, bool store_moments, int block_rows, int dense_obstacles,
-                             bool packed, bool index32, cudaStream_t st);
+                             bool packed, bool index32, bool pdl, cudaStream_t st);
 bool vec4_links_in_kernel(int block_rows, bool packed);
 
 // ---- auxiliary kernels (aux_kernels.cu) ----------------------------------------------------------

@@ -133,6 +133,7 @@ struct blbm_handle {
     unsigned long long graph_sig[4] = {0, 0, 0, 0}, graph_pending_sig[4] = {0, 0, 0, 0};
     bool graphs_primed = false;
     int use_graphs = -1;  // -1 auto (small lattices, no peers), 0 never, 1 always (when legal)
+    int use_pdl = -1;     // programmatic dependent launch of the fused vec4 step: -1 auto (where no graphs are), 0, 1
     float *rgb = nullptr;  // colour buffer (rows x W x 3), allocated by the first blbm_color_map
 };
 typedef blbm_handle blbm;

@@ -179,6 +179,13 @@ __device__ __forceinline__ void link_arrive(unsigned int *counter, const unsigne
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(epoch) : "memory");
     }
 }
+// Programmatic dependent launch: a step launched with the programmatic-serialization attribute may have its blocks
+// scheduled while the previous kernel on the stream drains (that kernel's blocks have all passed pdl_trigger or
+// exited); nothing of the previous kernel's results - nor anything it still reads - may be touched before pdl_wait
+// returns, which is when that kernel has completed and its stores are visible.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // own-row plane of staging slot q (the opposite of the directions that move in y)
 __host__ __device__ constexpr int stage_dir(int q) { return q == 0 ? D_NW : q == 1 ? D_N : q == 2 ? D_NE : q == 3 ? D_SW : q == 4 ? D_S : D_SE; }
 __host__ __device__ constexpr int stage_slot(int d) { return d == D_NW ? 0 : d == D_N ? 1 : d == D_NE ? 2 : d == D_SW ? 3 : d == D_S ? 4 : 5; }
@@ -199,6 +206,7 @@ __global__ void __launch_bounds__(32 * V4_ROWS, (DENSE || LINKED || MOM) ? 1024 
     // flag - a predicated load up front makes the in-order issue wait for the flag byte before the remaining pulls
     constexpr bool LATE_CLS = DENSE == 0;
     __shared__ float4 own_s[STAGED ? 6 : 1][STAGED ? 32 * V4_ROWS : 1];
+    if (!LINKED) pdl_trigger();  // the next step's blocks may be scheduled behind this kernel's last wave
     const uint32_t tid = threadIdx.y * 32u + threadIdx.x;
     const uint32_t nbx = gridDim.x;  // = ceil(P / 128)
     const uint32_t bx = blockIdx.x;
@@ -238,6 +246,7 @@ __global__ void __launch_bounds__(32 * V4_ROWS, (DENSE || LINKED || MOM) ? 1024 
     // issues in order and a predicated load waits for its predicate): the flag byte is requested first and
     // consumed LAST, after every independent load of the thread is in flight; the warp-edge floats are requested
     // with the pulls, not after the shuffles that wait for the pulls.
+    if (!LINKED) pdl_wait();  // first access to anything an earlier kernel wrote (or still reads)
     const uint8_t flag = EAGER_CLS ? (uint8_t)1 : p.rowflag[(size_t)r * nbx + bx];
     float le = 0.f, lne = 0.f, lse = 0.f, rw = 0.f, rnw = 0.f, rsw = 0.f;
     const bool edge_l = valid && lane == 0 && x4 != 0;
@@ -379,16 +388,24 @@ static bool plane_fits_u32(const StepParams &p) { return ((uint64_t)p.rows + 3u)
 bool vec4_links_in_kernel(int block_rows, bool packed) { return block_rows == 4 && !packed; }
 
 template <int V4_ROWS, int DENSE, bool PACKED, typename IDX, bool LINKED = false>
-static cudaError_t launch_vec4_idx(const StepParams &p, bool mom, cudaStream_t st)
+static cudaError_t launch_vec4_idx(const StepParams &p, bool mom, bool pdl, cudaStream_t st)
 {
     const uint32_t nbx = (p.P + 127u) / 128u;
     const uint32_t nrb = (p.rows + V4_ROWS - 1) / V4_ROWS;
     if (nbx == 0 || nrb == 0) return cudaErrorInvalidConfiguration;
     dim3 grid(nbx, nrb < GRID_Y ? nrb : GRID_Y, (nrb + GRID_Y - 1) / GRID_Y), block(32, V4_ROWS);
     if (grid.z > 65535u) return cudaErrorInvalidConfiguration;
-    if (mom) step_vec4_kernel<true, V4_ROWS, DENSE, PACKED, IDX, LINKED><<<grid, block, 0, st>>>(p);
-    else step_vec4_kernel<false, V4_ROWS, DENSE, PACKED, IDX, LINKED><<<grid, block, 0, st>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && !LINKED) ? 1 : 0;
+    if (mom) return cudaLaunchKernelEx(&cfg, step_vec4_kernel<true, V4_ROWS, DENSE, PACKED, IDX, LINKED>, p);
+    return cudaLaunchKernelEx(&cfg, step_vec4_kernel<false, V4_ROWS, DENSE, PACKED, IDX, LINKED>, p);
 }
 
 
@@ -396,37 +413,37 @@ static cudaError_t launch_vec4_idx(const StepParams &p, bool mom, cudaStream_t s
 // 64-bit offsets.
 template <int DENSE>
 static cudaError_t launch_vec4_flavour(const StepParams &p, bool mom, int block_rows, bool packed, bool index32,
-                                       cudaStream_t st)
+                                       bool pdl, cudaStream_t st)
 {
     if (p.link.sig_epoch != 0) {
         // in-kernel handshake: default block shape, scalar adds (vec4_links_in_kernel)
         if (block_rows != 4 || packed) return cudaErrorInvalidConfiguration;
-        if (index32 && plane_fits_u32(p)) return launch_vec4_idx<4, DENSE, false, uint32_t, true>(p, mom, st);
-        return launch_vec4_idx<4, DENSE, false, size_t, true>(p, mom, st);
+        if (index32 && plane_fits_u32(p)) return launch_vec4_idx<4, DENSE, false, uint32_t, true>(p, mom, false, st);
+        return launch_vec4_idx<4, DENSE, false, size_t, true>(p, mom, false, st);
     }
     switch (block_rows) {
-    case 1: return launch_vec4_idx<1, DENSE, false, size_t>(p, mom, st);
-    case 2: return launch_vec4_idx<2, DENSE, false, size_t>(p, mom, st);
-    case 8: return launch_vec4_idx<8, DENSE, false, size_t>(p, mom, st);
-    case 16: return launch_vec4_idx<16, DENSE, false, size_t>(p, mom, st);
+    case 1: return launch_vec4_idx<1, DENSE, false, size_t>(p, mom, pdl, st);
+    case 2: return launch_vec4_idx<2, DENSE, false, size_t>(p, mom, pdl, st);
+    case 8: return launch_vec4_idx<8, DENSE, false, size_t>(p, mom, pdl, st);
+    case 16: return launch_vec4_idx<16, DENSE, false, size_t>(p, mom, pdl, st);
     default: break;
     }
     if (index32 && plane_fits_u32(p))
-        return packed ? launch_vec4_idx<4, DENSE, true, uint32_t>(p, mom, st)
-                      : launch_vec4_idx<4, DENSE, false, uint32_t>(p, mom, st);
-    return packed ? launch_vec4_idx<4, DENSE, true, size_t>(p, mom, st)
-                  : launch_vec4_idx<4, DENSE, false, size_t>(p, mom, st);
+        return packed ? launch_vec4_idx<4, DENSE, true, uint32_t>(p, mom, pdl, st)
+                      : launch_vec4_idx<4, DENSE, false, uint32_t>(p, mom, pdl, st);
+    return packed ? launch_vec4_idx<4, DENSE, true, size_t>(p, mom, pdl, st)
+                  : launch_vec4_idx<4, DENSE, false, size_t>(p, mom, pdl, st);
 }
 
 cudaError_t launch_step_vec4(const StepParams &p, int mode, bool mom, int block_rows, int dense_obstacles,
-                             bool packed, bool index32, cudaStream_t st)
+                             bool packed, bool index32, bool pdl, cudaStream_t st)
 {
     if (mode != MODE_FUSED) return launch_step_scalar(p, mode, mom, st);
     switch (dense_obstacles) {
-    case 3: return launch_vec4_flavour<3>(p, mom, block_rows, packed, index32, st);
-    case 2: return launch_vec4_flavour<2>(p, mom, block_rows, packed, index32, st);
-    case 1: return launch_vec4_flavour<1>(p, mom, block_rows, packed, index32, st);
-    default: return launch_vec4_flavour<0>(p, mom, block_rows, packed, index32, st);
+    case 3: return launch_vec4_flavour<3>(p, mom, block_rows, packed, index32, pdl, st);
+    case 2: return launch_vec4_flavour<2>(p, mom, block_rows, packed, index32, pdl, st);
+    case 1: return launch_vec4_flavour<1>(p, mom, block_rows, packed, index32, pdl, st);
+    default: return launch_vec4_flavour<0>(p, mom, block_rows, packed, index32, pdl, st);
     }
 }
 

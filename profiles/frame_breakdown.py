@@ -49,6 +49,10 @@ timed("paint_only", paint)
 timed("paint+iterate15", lambda fr: (paint(fr), lbm.iterate(15)))
 timed("iterate15+readback", lambda fr: (lbm.iterate(15), lbm.read_output_async(out[fr & 1].data_ptr())))
 timed("full_frame", lambda fr: (paint(fr), lbm.iterate(15), lbm.read_output_async(out[fr & 1].data_ptr())))
+lbm.set_tuning(9, 0)  # steps launched plainly instead of as programmatic dependents of one another
+timed("iterate15_nopdl", lambda fr: lbm.iterate(15))
+timed("full_frame_nopdl", lambda fr: (paint(fr), lbm.iterate(15), lbm.read_output_async(out[fr & 1].data_ptr())))
+lbm.set_tuning(9, -1)
 lbm.set_tuning(5, 0)
 timed("iterate15_nographs", lambda fr: lbm.iterate(15))
 timed("full_frame_nographs", lambda fr: (paint(fr), lbm.iterate(15), lbm.read_output_async(out[fr & 1].data_ptr())))

@@ -25,6 +25,7 @@ pub const BLBM_TUNE_CUDA_GRAPHS: c_int = 5;
 pub const BLBM_TUNE_VEC4_PACKED: c_int = 6;
 pub const BLBM_TUNE_VEC4_INDEX32: c_int = 7;
 pub const BLBM_TUNE_LINK_IN_KERNEL: c_int = 8;
+pub const BLBM_TUNE_PDL: c_int = 9;
 
 extern "C" {
     pub fn blbm_last_error() -> *const c_char;

@@ -467,8 +467,8 @@ def _fuzz_walk(lbm, ora, rng, w, h, tag, tunable, nops, log):
             log.append(('lazy', lz))
             lbm.set_lazy_barriers(lz)
         elif op == 11:
-            knob = int(rng.choice([0, 4, 5, 6, 7]))
-            val = {0: [1, 2, 4, 8, 16], 4: [-1, 0, 1, 2, 3], 5: [-1, 0, 1], 6: [0, 1], 7: [-1, 0, 1]}[knob]
+            knob = int(rng.choice([0, 4, 5, 6, 7, 9]))
+            val = {0: [1, 2, 4, 8, 16], 4: [-1, 0, 1, 2, 3], 5: [-1, 0, 1], 6: [0, 1], 7: [-1, 0, 1], 9: [-1, 0, 1]}[knob]
             kv = int(rng.choice(val))
             log.append(('knob', knob, kv))
             lbm.set_tuning(knob, kv)
@@ -666,15 +666,19 @@ def test_paint_frames_never_synchronise_and_stay_exact():
 
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("w,h", [(150, 40), (256, 33)])
-def test_every_graph_run_length_with_and_without_the_moment_tail(kernel, w, h):
+@pytest.mark.parametrize("pdl", [1, 0])
+def test_every_graph_run_length_with_and_without_the_moment_tail(kernel, w, h, pdl):
     """Small lattices replay runs of 2, 4 .. 16 steps as CUDA graphs, the call's moment-storing last step included when
     the run ends the call and not when it does not (longer calls); a stroke of at most 64 cells is
     ONE launch that updates the mask and rebuilds the class words (every block applies the whole stroke before it reads
     the mask), leaving a class swap pending for the first step of the next graph.  Calls of every length 1..35 from
     both start parities, with and without such a stroke in front, strokes on the inlet / outlet columns and on rows
-    0 / H-1 and repeated cells (last writer wins), against the oracle after every call."""
+    0 / H-1 and repeated cells (last writer wins), against the oracle after every call; with the steps launched as
+    programmatic dependents of one another (a step's blocks are scheduled while the previous one drains and wait for
+    its completion before they touch memory: the default outside graphs) and plainly."""
     om = omega_from_viscosity(0.02)
     lbm, ora = LBM(om, w, h, inflow_ux=0.08, kernel=kernel, lazy_barriers=0), Oracle(om, w, h, inflow_ux=0.08)
+    lbm.set_tuning(9, pdl)
     rng = np.random.default_rng(w)
     lbm.iterate(1); ora.iterate(1)  # the graphs are captured by the first call that could use one: make it this one
     lbm.iterate(5); ora.iterate(5)
