@@ -28,7 +28,9 @@
  * blbm_create() makes the whole-lattice slab.  Slabs of one lattice are linked to their neighbours
  * (same process: blbm_link_local; other process: blbm_export_peer / blbm_link_peer) and then exchange
  * the one-row halos of the three crossing populations per face by direct NVLink stores issued from
- * the step kernel itself.  Read-backs and writes address the slab's own rows only.
+ * the step kernel itself.  Read-backs and writes address the slab's own rows only.  Linked slabs advance an
+ * epoch counter per halo-exchanging launch and per summary: every slab of a lattice must be given the same
+ * sequence of stepping, half-step, reset and summary calls (a group handle does that by construction).
  */
 #ifndef BLBM_H
 #define BLBM_H

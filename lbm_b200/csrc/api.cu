@@ -333,7 +333,14 @@ int run_summary(blbm *h)
     if (h->copy_pending) CK(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));  // the copy still reads `out`
     CK(launch_summary(h->stat, h->mx, h->my, h->rho, h->out, geom(h), h->stream));
     h->launches++;
-    return BLBM_OK;
+    // Linked slabs: the summary is part of the epoch protocol.  curl READS the moment halo rows, and the neighbours'
+    // next moment-storing launch overwrites them; that launch only waits for our previous *pushing* launch, which is
+    // stream-ordered BEFORE this kernel - so a one-step iterate or a public collide half-step right after an iterate
+    // could overtake a summary still pending here (seen once in 400 random walks, with four processes time-slicing
+    // the GPU: one boundary row of the curl field computed from the next call's moments).  Publishing an epoch after
+    // the summary makes every later push into our halo rows wait for it.  (Every slab runs the same calls, so the
+    // epochs stay in step.)
+    return signal_peers(h);
 }
 
 // all even: a call's runs share one start parity; every even length, so that the 14 graph-able steps of a 15-step

@@ -565,6 +565,39 @@ def _group_devices(n):
     return list(range(n)) if ndev >= n else [0] * n
 
 
+@pytest.mark.parametrize("in_kernel", [1, 0])
+@pytest.mark.parametrize("ahead", [0, 1])
+def test_a_slab_running_ahead_cannot_overtake_its_neighbours_pending_summary(in_kernel, ahead):
+    """The summary is part of the epoch protocol of linked slabs.  curl reads the moment halo rows; the neighbour's next
+    moment-storing launch (here: the public collide half-step right after an iterate) overwrites them and used to wait
+    only for this slab's previous *pushing* launch, which is stream-ordered before the summary - a slab running ahead
+    (an unsynchronised rank of a multi-process job; once in 400 random walks with four processes time-slicing one
+    GPU) computed one boundary row of the neighbour's curl field from the next call's moments.  Driven
+    deterministically here through the slab views of a group: slab `ahead` is given its iterate AND its collide before
+    the other slab is given its summary.  Every slab still sees the same call sequence; nothing blocks on the host."""
+    w, h = 96, 28
+    om = omega_from_viscosity(0.02)
+    grp = LBM(om, w, h, inflow_ux=0.09, devices=_group_devices(2), kernel=Kernel.Vec4, lazy_barriers=0)
+    grp.set_tuning(8, in_kernel)
+    ora = Oracle(om, w, h, inflow_ux=0.09)
+    pts = disc_pairs(w, 30, 14, 4).astype(np.uint32)  # a disc across the slab boundary: the wake makes curl non-trivial
+    grp.draw_points(pts); ora.draw_points(pts)
+    grp.iterate(40); ora.iterate(40)
+    compare_state(grp, ora, "before the skewed calls")
+    fast, slow = grp.slab(ahead), grp.slab(1 - ahead)
+    for n in (3, 1, 2):
+        fast.iterate(n)   # steps + summary of the slab that runs ahead
+        slow.advance(n)   # the other slab's steps (its moment-storing launch pushes into fast's halo rows) ...
+        fast.collide()    # ... fast's NEXT moment push, enqueued before slow's summary exists
+        slow.rerender()   # slow's summary of the iterate: must still see the moments of that iterate in its halo rows
+        slow.collide()
+        ora.iterate(n); ora.collide()
+        compare_state(grp, ora, f"skewed iterate({n}) + collide, slab {ahead} ahead, in_kernel={in_kernel}")
+    grp.iterate(9); ora.iterate(9)
+    compare_state(grp, ora, "back in step")
+    grp.close()
+
+
 @pytest.mark.parametrize("nslabs", [2, 3, 5])
 def test_group_handle_spans_the_whole_api(nslabs):
     """blbm_create_group: ONE handle over n linked slabs.  Everything a caller of the reference's `LBM` does —
