@@ -1060,7 +1060,14 @@ int blbm_stream(blbm_t *h)
     rc = materialise(h);
     if (rc) return rc;
     const int x = (int)(h->step % 2), y = (int)((h->step + 1) % 2);
-    return launch_step(h, MODE_STREAM_ONLY, x, y, false);
+    rc = launch_step(h, MODE_STREAM_ONLY, x, y, false);
+    if (rc) return rc;
+    // Like the summary, the public stream half-step READS halo rows without pushing anything: publish an epoch, so
+    // that a neighbour running ahead cannot start the next collide - whose boundary rows go into the halo rows this
+    // launch gathers from - before it is done.  (materialise()'s stream-only launch needs none: whatever the next
+    // pushing launch of a neighbour is, it writes the other buffer's halo rows or waits for a launch of ours that is
+    // stream-ordered after it - which keeps read-backs on one slab alone legal.)
+    return signal_peers(h);
 }
 
 int blbm_set_summary(blbm_t *h, int stat)

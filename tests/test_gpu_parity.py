@@ -593,6 +593,12 @@ def test_a_slab_running_ahead_cannot_overtake_its_neighbours_pending_summary(in_
         slow.collide()
         ora.iterate(n); ora.collide()
         compare_state(grp, ora, f"skewed iterate({n}) + collide, slab {ahead} ahead, in_kernel={in_kernel}")
+    # the public half-steps: stream READS the halo rows the neighbour's next collide stores into
+    for k in range(3):
+        fast.stream(); fast.collide()
+        slow.stream(); slow.collide()
+        ora.stream(); ora.collide()
+        compare_state(grp, ora, f"skewed stream + collide #{k}, slab {ahead} ahead, in_kernel={in_kernel}")
     grp.iterate(9); ora.iterate(9)
     compare_state(grp, ora, "back in step")
     grp.close()
