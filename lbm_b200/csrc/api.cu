@@ -1544,6 +1544,12 @@ int blbm_exchange_halos(blbm_t *h)
     if (rc) return rc;
     rc = materialise(h);
     if (rc) return rc;
+    // A barrier before the pushes: the rows about to be sent may have been rewritten (blbm_write_population), and the
+    // neighbour may still have a stream pass queued that gathers the old ones from its halo rows (materialise()
+    // publishes nothing).  Our epoch tells the neighbours that everything WE still had to read from our halo rows is
+    // done; push_all_halos then waits for theirs.  (Found by tests/test_epoch_protocol_model.py.)
+    rc = signal_peers(h);
+    if (rc) return rc;
     return push_all_halos(h);
 }
 
