@@ -1,7 +1,7 @@
 """The epoch protocol of linked slabs, as a happens-before model (CPU; no GPU, no library call).
 
-Two slabs A (above) and B (below) of one lattice store into each other's halo rows from their own streams and order
-those stores with one 64-bit epoch word per face.  A GPU soak with four processes time-slicing one
+Neighbouring slabs of one lattice (a chain A above B above C ...) store into each other's halo rows from their own
+streams and order those stores with one 64-bit epoch word per face.  A GPU soak with four processes time-slicing one
 device found a hole in that protocol once in 400 random walks; the hole is a property of WHICH launches wait for and
 publish epochs, not of any kernel, so it can be checked without a GPU: this file restates, call by call, the
 wait / launch / signal sequence that lbm_b200/csrc/api.cu enqueues (sync_peers, signal_peers, push_all_halos,
@@ -30,8 +30,10 @@ FUSED, COLLIDE, STREAM = "fused", "collide-only", "stream-only"
 class Slab:
     """host-side state of one slab handle and the operations its calls enqueue on its stream"""
 
-    def __init__(self, name, other, in_kernel=True, summary_epoch=True, stream_epoch=True, exchange_epoch=True):
-        self.name, self.other = name, other  # other: name of the neighbour (the owner of the halo rows we store into)
+    def __init__(self, name, up=None, dn=None, in_kernel=True, summary_epoch=True, stream_epoch=True,
+                 exchange_epoch=True):
+        self.name = name
+        self.nbr = {side: n for side, n in (("up", up), ("dn", dn)) if n}  # the slabs above / below, if any
         self.in_kernel, self.summary_epoch, self.stream_epoch = in_kernel, summary_epoch, stream_epoch
         self.exchange_epoch = exchange_epoch
         self.regimeT, self.step, self.halo_dirty = False, 0, True  # blbm_link_*: halo_dirty = true
@@ -43,16 +45,16 @@ class Slab:
         """a kernel of ours rewrites our own rows of that plane: what a later push copies is a new value"""
         self.ver[(kind, buf)] += 1
 
+    # regions: (owner of the memory, which of its two halos, kind, buffer)
     def pushed(self, kind, buf=None):
-        """region in the neighbour's memory -> tag of the rows we copy there"""
-        return {self.theirs(kind, buf): (self.name, kind, buf, self.ver[(kind, buf)])}
+        """regions in the neighbours' memory -> tag of the rows we copy there (our first row into the lower halo of
+        the slab above, our last row into the upper halo of the slab below)"""
+        return {(n, "dn" if side == "up" else "up", kind, buf): (self.name, side, kind, buf, self.ver[(kind, buf)])
+                for side, n in self.nbr.items()}
 
-    # regions: (owner of the memory, kind, buffer)
     def own(self, kind, buf=None):
-        return (self.name, kind, buf)
-
-    def theirs(self, kind, buf=None):
-        return (self.other, kind, buf)
+        """our halo rows that a gather of ours reads"""
+        return {(self.name, side, kind, buf) for side in self.nbr}
 
     # ---- api.cu: sync_peers / signal_peers / push_all_halos --------------------------------------------------
     def sync_peers(self):
@@ -77,7 +79,7 @@ class Slab:
         pushes = mode != STREAM
         if self.halo_dirty and mode != COLLIDE:
             self.push_all_halos()
-        reads = {self.own("pop", xbuf)} if mode in (FUSED, STREAM) else set()
+        reads = self.own("pop", xbuf) if mode in (FUSED, STREAM) else set()
         self.touch("pop", ybuf)  # every mode rewrites our rows of buffer y
         writes = dict(self.pushed("pop", ybuf)) if pushes else {}
         if pushes and mom:
@@ -117,7 +119,7 @@ class Slab:
 
     def run_summary(self):
         self.sync_peers()
-        self.ops.append(("kernel", "summary (curl)", {self.own("mom")}, {}))
+        self.ops.append(("kernel", "summary (curl)", self.own("mom"), {}))
         if self.summary_epoch:
             self.signal_peers()
 
@@ -143,8 +145,8 @@ class Slab:
             self.sync_peers()
             for key in self.ver:
                 self.touch(*key)
-            self.ops.append(("kernel", "fill", set(), {self.own(*key): (self.name, "fill", key, self.ver[key])
-                                                      for key in self.ver}))
+            self.ops.append(("kernel", "fill", set(), {region: (self.name, "fill", key, self.ver[key])
+                                                      for key in self.ver for region in self.own(*key)}))
             self.step, self.regimeT, self.halo_dirty = 0, False, False
             self.signal_peers()
         elif what == "readback":  # read_population & co: brings both buffers to the reference's state, own rows only
@@ -162,38 +164,41 @@ class Slab:
             raise ValueError(what)
 
 
-def happens_before(a, b):
-    """vector clocks of every operation of both streams; returns (clocks, deadlock) - a wait for epoch e is released
-    by the neighbour's first signal with a value >= e"""
-    slabs = {"A": a, "B": b}
-    clocks = {"A": [], "B": []}
-    done = {"A": 0, "B": 0}
-    cur = {"A": [0, 0], "B": [0, 0]}
-    idx = {"A": 0, "B": 1}
+def happens_before(slabs):
+    """vector clocks of every operation of every stream; returns (clocks, deadlock) - a wait for epoch e is released
+    once every neighbour's first signal with a value >= e has been issued"""
+    names = list(slabs)
+    clocks = {n: [] for n in names}
+    done = {n: 0 for n in names}
+    cur = {n: [0] * len(names) for n in names}
     progress = True
     while progress:
         progress = False
-        for me, other in (("A", "B"), ("B", "A")):
+        for me in names:
             while done[me] < len(slabs[me].ops):
                 op = slabs[me].ops[done[me]]
                 if op[0] == "wait" and op[1] > 0:
-                    sig = next((k for k, o in enumerate(slabs[other].ops) if o[0] == "signal" and o[1] >= op[1]), None)
-                    if sig is None or sig >= done[other]:
+                    sigs = {}
+                    for other in slabs[me].nbr.values():
+                        sigs[other] = next((k for k, o in enumerate(slabs[other].ops)
+                                            if o[0] == "signal" and o[1] >= op[1]), None)
+                    if any(k is None or k >= done[o] for o, k in sigs.items()):
                         break  # not published yet
-                    cur[me] = [max(x, y) for x, y in zip(cur[me], clocks[other][sig])]
+                    for o, k in sigs.items():
+                        cur[me] = [max(x, y) for x, y in zip(cur[me], clocks[o][k])]
                 cur[me] = list(cur[me])
-                cur[me][idx[me]] += 1
+                cur[me][names.index(me)] += 1
                 clocks[me].append(tuple(cur[me]))
                 done[me] += 1
                 progress = True
-    deadlock = any(done[s] < len(slabs[s].ops) for s in slabs)
+    deadlock = any(done[n] < len(slabs[n].ops) for n in names)
     return clocks, deadlock
 
 
-def races(a, b):
-    """accesses of the two streams to the same halo region, at least one of them a store, with no happens-before
+def races(slabs):
+    """accesses of different streams to the same halo region, at least one of them a store, with no happens-before
     between them - except a store that re-sends the version the region already holds for the racing gather"""
-    clocks, deadlock = happens_before(a, b)
+    clocks, deadlock = happens_before(slabs)
     if deadlock:
         return ["deadlock"]
 
@@ -201,7 +206,7 @@ def races(a, b):
         return p != q and all(x <= y for x, y in zip(p, q))
 
     reads, writes = [], []
-    for s, slab in (("A", a), ("B", b)):
+    for s, slab in slabs.items():
         for k, op in enumerate(slab.ops):
             if op[0] == "kernel":
                 reads += [(region, s, clocks[s][k], op[1]) for region in op[2]]
@@ -224,13 +229,19 @@ def races(a, b):
     return found
 
 
-def run(calls_a, calls_b=None, **kw):
-    a, b = Slab("A", "B", **kw), Slab("B", "A", **kw)
-    for c in calls_a:
-        a.call(c)
-    for c in (calls_a if calls_b is None else calls_b):
-        b.call(c)
-    return races(a, b)
+def chain(n, **kw):
+    names = "ABCDE"[:n]
+    return {c: Slab(c, up=names[i - 1] if i else None, dn=names[i + 1] if i + 1 < n else None, **kw)
+            for i, c in enumerate(names)}
+
+
+def run(calls_a, calls_b=None, nslabs=2, **kw):
+    """slab A is given calls_a, every other slab calls_b (default: the same calls)"""
+    slabs = chain(nslabs, **kw)
+    for name, slab in slabs.items():
+        for c in (calls_a if name == "A" or calls_b is None else calls_b):
+            slab.call(c)
+    return races(slabs)
 
 
 CALLS = ["iterate1", "iterate2", "iterate3", "advance1", "advance2", "collide", "stream", "rerender", "reset",
@@ -250,19 +261,33 @@ def test_every_call_sequence_up_to_four_calls_is_race_free(in_kernel):
 
 
 @pytest.mark.parametrize("in_kernel", [True, False])
-def test_long_random_call_sequences_with_stray_read_backs_are_race_free(in_kernel):
+@pytest.mark.parametrize("nslabs", [2, 3, 4])
+def test_long_random_call_sequences_with_stray_read_backs_are_race_free(in_kernel, nslabs):
+    """chains of 2-4 slabs (a middle slab waits for and publishes to two neighbours), 5-12 calls, read-backs strewn
+    over each slab independently"""
     import random
-    rng = random.Random(20230)
+    rng = random.Random(20230 + nslabs)
     base = [c for c in CALLS if c != "readback"]
-    for _ in range(1500):
+    for _ in range(600):
         seq = [rng.choice(base) for _ in range(rng.randint(5, 12))]
+        slabs = chain(nslabs, in_kernel=in_kernel)
         calls = {}
-        for s in "AB":
-            calls[s] = list(seq)
-            for _ in range(rng.randint(0, 3)):  # read-backs wherever a rank likes, independently of its neighbour
-                calls[s].insert(rng.randint(0, len(calls[s])), "readback")
-        found = run(calls["A"], calls["B"], in_kernel=in_kernel)
-        assert not found, f"A {calls['A']} / B {calls['B']}: {found[:3]}"
+        for name, slab in slabs.items():
+            calls[name] = list(seq)
+            for _ in range(rng.randint(0, 3)):  # read-backs wherever a rank likes, independently of its neighbours
+                calls[name].insert(rng.randint(0, len(calls[name])), "readback")
+            for c in calls[name]:
+                slab.call(c)
+        found = races(slabs)
+        assert not found, f"{calls}: {found[:3]}"
+
+
+@pytest.mark.parametrize("in_kernel", [True, False])
+def test_every_call_sequence_up_to_three_calls_on_three_slabs(in_kernel):
+    for length in (1, 2, 3):
+        for seq in itertools.product(CALLS, repeat=length):
+            found = run(seq, nslabs=3, in_kernel=in_kernel)
+            assert not found, f"{seq}: {found[:3]}"
 
 
 @pytest.mark.parametrize("in_kernel", [True, False])
@@ -294,6 +319,6 @@ def test_the_model_reports_the_races_of_the_protocol_before_the_fixes(in_kernel)
     found = run(("iterate1", "restore"), in_kernel=in_kernel, exchange_epoch=False)
     assert any("'pop'" in f and "stream-only" in f and "push_all_halos" in f for f in found), found
     # a waiter without a matching signal is reported, not looped on
-    a, b = Slab("A", "B"), Slab("B", "A")
-    a.call("iterate2")
-    assert races(a, b) == ["deadlock"]
+    slabs = chain(2)
+    slabs["A"].call("iterate2")
+    assert races(slabs) == ["deadlock"]
