@@ -21,6 +21,7 @@ a third one of the same family (write_population + exchange_halos against a neig
 by the model itself and closed the same way.
 """
 import itertools
+import os
 
 import pytest
 
@@ -248,16 +249,19 @@ CALLS = ["iterate1", "iterate2", "iterate3", "advance1", "advance2", "collide", 
          "readback", "restore"]
 
 
+DEPTH = int(os.environ.get("BLBM_PROTOCOL_MODEL_DEPTH", "4"))  # 5: 177,155 sequences, a few minutes (soak)
+
+
 @pytest.mark.parametrize("in_kernel", [True, False])
 def test_every_call_sequence_up_to_four_calls_is_race_free(in_kernel):
     """both slabs are given the same calls (include/blbm.h: the rule for linked slabs); any relative speed"""
     n = 0
-    for length in (1, 2, 3, 4):
+    for length in range(1, DEPTH + 1):
         for seq in itertools.product(CALLS, repeat=length):
             found = run(seq, in_kernel=in_kernel)
             assert not found, f"{seq}: {found[:3]}"
             n += 1
-    assert n == sum(len(CALLS) ** k for k in (1, 2, 3, 4))
+    assert n == sum(len(CALLS) ** k for k in range(1, DEPTH + 1))
 
 
 @pytest.mark.parametrize("in_kernel", [True, False])
