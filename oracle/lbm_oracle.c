@@ -30,7 +30,14 @@
  * three moment arrays and a u32 barrier mask, every intermediate going through fp32 memory exactly
  * where the WGSL stores it.  Compile with -O2 -ffp-contract=off (no FMA contraction), no fast-math.
  * Semantics where WebGPU is implementation-defined: out-of-range reads return 0 / 0.0f, out-of-range
- * writes are dropped (robust-buffer-access behaviour).
+ * writes are dropped (robust-buffer-access behaviour: what a Vulkan device with robustBufferAccess2 - lavapipe, the
+ * backend SURVEY.md section 8 names - does).  lbm_oracle_set_oob_clamp(o, 1) selects the other behaviour the WebGPU
+ * specification allows and browsers implement (Tint's robustness transform, naga's `Restrict` policy): the index is
+ * clamped, min(u32(index), length - 1).  It is NOT a corner case: cell (W-1, H-2) pulls its north-west-moving
+ * population from index W*H every step - 0.0 under the first policy, a bounce-back off the wall cell (W-1, H-1) under
+ * the second - and the difference spreads over the whole field.  The mode exists so that the
+ * difference can be measured and a future parity target that clamps has an oracle; the CUDA path implements the
+ * first policy only.
  *
  * Reference files followed (paths relative to /root/reference/lbm-wgpu/src):
  *   lbm.rs:595-609     init_barrier, index_pre_init
@@ -90,6 +97,7 @@ typedef struct lbm_oracle {
     float omega;
     uint64_t step;        /* compute_step */
     int stat;             /* summary_stat */
+    int oob_clamp;        /* 0 (default): out-of-range reads return 0; 1: they return the last element (see below) */
 } lbm_oracle;
 
 /* ---- lbm.rs:611-643 set_equil: nine uniform equilibrium values, fp32, op order as written ---- */
@@ -268,6 +276,8 @@ static void collide_cardinal(lbm_oracle *o, int c)
     }
 }
 
+void lbm_oracle_set_oob_clamp(lbm_oracle *o, int clamp) { o->oob_clamp = clamp != 0; }
+
 void lbm_oracle_collide(lbm_oracle *o)
 {
     int c = (int)(o->step % 2);
@@ -280,11 +290,13 @@ void lbm_oracle_collide(lbm_oracle *o)
 /* ---- the four stream passes, lbm.rs:1127-1134; one generic body for the four WGSL files ---- */
 static inline uint32_t bar_at(const lbm_oracle *o, int64_t j)
 {
-    return (j < 0 || j >= o->n) ? 0u : o->bar[j];
+    if (j < 0 || j >= o->n) return o->oob_clamp ? o->bar[o->n - 1] : 0u; /* (a negative index is a huge u32) */
+    return o->bar[j];
 }
 static inline float pop_at(const lbm_oracle *o, const float *p, int64_t j)
 {
-    return (j < 0 || j >= o->n) ? 0.0f : p[j];
+    if (j < 0 || j >= o->n) return o->oob_clamp ? p[o->n - 1] : 0.0f;
+    return p[j];
 }
 
 /* population `a` travels by +off per step, `b` by -off (e_w_stream.wgsl:25-64 with a=e, b=w, off=+1) */

@@ -68,6 +68,7 @@ def lib(contract=None):
         L.lbm_oracle_threads.restype = C.c_int
         L.lbm_oracle_set_threads.argtypes = [C.c_int]
         L.lbm_oracle_contract.restype = C.c_int
+        L.lbm_oracle_set_oob_clamp.argtypes = [P, C.c_int]
         assert bool(L.lbm_oracle_contract()) == contract
         _libs[contract] = _lib = L
     return _lib
@@ -95,12 +96,17 @@ def use_all_cores():
 
 
 class Oracle:
-    def __init__(self, omega, x, y, inflow_ux=0.1, contract=None):
+    def __init__(self, omega, x, y, inflow_ux=0.1, contract=None, oob="zero"):
+        """oob: what an out-of-range read returns - "zero" (the defined semantics) or "clamp"
+        (the last element: the other behaviour WebGPU allows; sensitivity studies only, no CUDA counterpart)"""
         self.w, self.h = int(x), int(y)
         self._L = lib(contract)
         self._h = self._L.lbm_oracle_create(self.w, self.h, float(omega), float(inflow_ux))
         if not self._h:
             raise MemoryError("lbm_oracle_create failed")
+        if oob not in ("zero", "clamp"):
+            raise ValueError(oob)
+        self._L.lbm_oracle_set_oob_clamp(self._h, 1 if oob == "clamp" else 0)
 
     def close(self):
         if self._h:

@@ -54,6 +54,9 @@ def _is_int(v):
     return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
 
 
+OOB_POLICY = "zero"  # "clamp": sensitivity study of the other legal out-of-range-read behaviour (see _Lanes._load)
+
+
 class Vec3:
     """vec3<T>: three components, each a per-lane array or a uniform / abstract scalar"""
 
@@ -237,6 +240,17 @@ class _Lanes:
     def _load(self, name, idx, active):
         data = self.d.arrays[name]
         m = len(data)
+        if OOB_POLICY == "clamp" and m > 0:
+            # the other thing a WebGPU backend may do with an out-of-range read (naga's `Restrict` policy, Tint's
+            # robustness transform): min(u32(index), length - 1).  Sensitivity study only (tests/test_wgsl_pin.py);
+            # the oracle's and the product's semantics are "reads return 0" (SURVEY.md section 8).
+            if not isinstance(idx, np.ndarray):
+                return data[min(int(idx) & 0xFFFFFFFF, m - 1)]
+            if not self._is_own(idx, active):
+                self.d.foreign.add(name)
+                if name in self.d.stored:
+                    raise self.d.conflict(name)
+            return data[np.minimum(idx.astype(np.int64) & 0xFFFFFFFF, m - 1)]
         if idx is self.gid:
             if m >= self.hi:
                 return data[self.lo:self.hi].copy()
